@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — Lanczos e^A·x throughput on B200 (BASELINE.json metric: Lanczos iterations/s + SpMV GB/s vs HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one full e^A·x evaluation on the workload graph: k Lanczos steps (fused SpMV+alpha, fused update+norm,
+scale), the on-device tridiagonal eigen-solve + coefficient vector, and multOut — i.e. what parallel-final/main.cu:115-127
+times, with the start vector already resident in HBM. `value` = k*K / (device time of K steps), max over ranks.
+`e2e` = the same through the reference-facing call lz_expv_host with pinned HOST buffers (H2D of x and D2H of e^A x inside
+the timed region). PyTorch is used only for torch.distributed plumbing and pinned host memory.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+METRIC, UNIT = "lanczos_iterations_per_sec", "iterations/s"
+
+# BASELINE.json configs. `k`/`reorth` are the config's; the default bench line uses plain Lanczos
+# (what the reference computes and what the roofline formula 4*nnz + 68*n describes) and reports the config's
+# full-reorthogonalisation variant next to it under "detail".
+WORKLOADS = {
+    "c1": dict(kind="er", n=10000, m=50000, seed=20261018, k=20, reorth=False, name="C1 ER n=10k deg10 k=20"),
+    "c2": dict(kind="rmat", scale=20, ef=8, seed=1, k=30, reorth=False, name="C2 R-MAT 2^20 ef8 k=30"),
+    "c3": dict(kind="rmat", scale=24, ef=8, seed=1, k=50, reorth=True, name="C3 R-MAT 2^24 ef8 k=50"),
+    "c4": dict(kind="rmat", scale=27, ef=8, seed=1, k=50, reorth=False, name="C4 R-MAT 2^27 ef8 k=50"),
+    "c5": dict(kind="band", n=1 << 28, seed=5, k=100, reorth=False, name="C5 banded 2^28 k=100"),
+}
+
+
+def make_spec(lz, w, scale_override=None):
+    if w["kind"] == "rmat":
+        return lz.GraphSpec.rmat(scale_override or w["scale"], w["ef"], w["seed"])
+    if w["kind"] == "er":
+        return lz.GraphSpec.er(w["n"], w["m"], w["seed"])
+    return lz.GraphSpec.band(w["n"], w["seed"])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per SpMV launch from the committed ncu --set full capture of this workload, if there is one."""
+    p = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+def cpu_reference_sample(orc, csr_path, n, nnz, iters, reps=1):
+    """Times the reference's own CPU Lanczos (oracle/_ref/ref_final = lanczosDecomp<double>(A, iters, ones, cuda=false),
+    parallel-final/lib/lanczos.cu:17-60, single-threaded) on `iters` steps of the workload graph. Falls back to the C
+    restatement (oracle/lanczos_oracle.c) when the compiled reference is not there."""
+    if orc.have_ref():
+        r = orc.run_ref_final(None, None, iters, iters=iters, reps=reps, want_output=False, csr_path=csr_path)
+        vals = [t["iters_per_s"] for t in r["timings"]]
+        secs = [t["lanczos_s"] for t in r["timings"]]
+        return vals, secs, "reference"
+    lz = graft.load_package()
+    _, ro, ci = lz.read_bin(csr_path)
+    vals, secs = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.lanczos(ro, ci, iters, np.ones(n))
+        dt = time.perf_counter() - t0
+        vals.append(iters / dt); secs.append(dt)
+    return vals, secs, "port"
+
+
+def sample_iters_for(nnz):
+    # ~1e-8 s per stored entry per CPU iteration at large n (measured: 108 ms/iter at nnz 1.68e7) -> aim for ~10-15 s
+    per_iter = max(nnz * 1.2e-8, 1e-4)
+    return int(min(50, max(2, round(12.0 / per_iter))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=int, default=None, help="override the R-MAT scale (debug)")
+    ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reorth-detail", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    w = dict(WORKLOADS[args.workload])
+    k = args.k or w["k"]
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    lz = graft.load_package()
+    orc = graft.load_oracle()
+
+    # ---------------------------------------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        spec = make_spec(lz, w, args.scale)
+        csr_path = os.path.join(tempfile.gettempdir(), f"lz_bench_{args.workload}_{args.scale or ''}.bin")
+        try:
+            with lz.Context(local_rank) as ctx:           # input construction only (not timed, not on the measured path)
+                ctx.graph_generate(spec)
+                ro, ci = ctx.csr_download()
+        except lz.LzError:
+            _, ro, ci = lz.generate_host(spec)
+        n, nnz = len(ro) - 1, int(ro[-1])
+        lz.write_bin(csr_path, ro, ci)
+        del ro, ci
+        m = sample_iters_for(nnz)
+        total = args.steps + args.warmup
+        vals, secs, kind = cpu_reference_sample(orc, csr_path, n, nnz, m, reps=total)
+        os.unlink(csr_path)
+        vals, secs = vals[args.warmup:], secs[args.warmup:]
+        value = m * len(secs) / sum(secs)
+        sample = f"{m} Lanczos steps of {w['name']} per step (lanczosDecomp<double>(A,{m},ones,cuda=false)), 1 thread"
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["name"], "n": n, "nnz": nnz, "k": k, "reorth": "none", "sample_iters": m},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------------------------------------------ our arm
+    import torch
+    dist = None
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [lz.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+
+    def barrier():
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = lz.Context(local_rank, rank, world, uid)
+    spec = make_spec(lz, w, args.scale)
+    t0 = time.perf_counter()
+    ctx.graph_generate(spec)
+    ctx.sync()
+    t_graph = time.perf_counter() - t0
+    gi = ctx.graph_info()
+    n, nnz = gi.n, gi.nnz
+    ctx.set_start_vector(None)                     # x = ones resident in HBM (main.cu:79)
+    ctx.lanczos_run(k)                             # allocates the basis
+    ctx.sync()
+
+    def step():
+        ctx.lanczos_run(k)
+        ctx.tridiag_expv()
+        ctx.multout()
+
+    launches0 = None
+    for _ in range(warmup):
+        step()
+    ctx.sync()
+    ctx.set_profiling(True)
+    step(); ctx.sync()                             # one profiled warm-up so event creation is outside the timed region
+    launches0 = ctx.timings().kernel_launches
+    sampler = ClockSampler(local_rank)
+    barrier(); ctx.sync()
+    sampler.start()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_stop()
+    ctx.sync(); barrier()
+    clocks = sampler.stop()
+    tm = ctx.timings()
+    launches = tm.kernel_launches - launches0
+    ms = max_over_ranks(ms)
+    value = k * args.steps / (ms * 1e-3)
+    ctx.set_profiling(False)
+
+    # lanczos-only and multOut-only numbers of the last step
+    detail = {"lanczos_ms": tm.lanczos_ms, "tridiag_ms": tm.tridiag_ms, "multout_ms": tm.multout_ms,
+              "spmv_ms_avg": tm.spmv_ms_avg, "update_scale_ms_per_iter": tm.update_ms_avg, "comm_ms_per_iter": tm.comm_ms_avg,
+              "lanczos_only_iters_per_s": k / (tm.lanczos_ms * 1e-3) if tm.lanczos_ms else None,
+              "graph_build_s": t_graph, "max_degree": gi.max_degree, "empty_rows": gi.empty_rows}
+
+    # roofline of the dominant kernel (k_spmv_dot): algorithmic bytes 4*nnz + 20*n per launch, per GPU
+    peak, peak_src = measured_peak()
+    b_spmv = 4.0 * gi.nnz_local + 4.0 * gi.n_local + 8.0 * n + 8.0 * gi.n_local   # == 4 nnz + 20 n at world == 1
+    spmv_gbs = b_spmv / (tm.spmv_ms_avg * 1e-3) / 1e9 if tm.spmv_ms_avg else None
+    roofline = {"bound": "hbm", "kernel": "k_spmv_dot", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
+                "frac": (spmv_gbs / peak) if spmv_gbs else None, "traffic": ncu_traffic(args.workload),
+                "algorithmic_bytes_per_launch": b_spmv, "peak_source": peak_src}
+    b_iter = 4.0 * gi.nnz_local + 68.0 * gi.n_local
+    detail["iteration_roofline_iters_per_s"] = peak * 1e9 / b_iter
+    detail["iteration_frac_of_roofline"] = (k / (tm.lanczos_ms * 1e-3)) / (peak * 1e9 / b_iter) if tm.lanczos_ms else None
+    b_mult = 8.0 * gi.n_local * k + 8.0 * gi.n_local
+    detail["multout_gbs"] = b_mult / (tm.multout_ms * 1e-3) / 1e9 if tm.multout_ms else None
+
+    # the config's full-reorthogonalisation variant (C3), reported next to the headline
+    if w.get("reorth") and not args.no_reorth_detail:
+        ctx.lanczos_run(k, lz.REORTH_FULL); ctx.sync()
+        barrier()
+        ctx.timer_start()
+        ctx.lanczos_run(k, lz.REORTH_FULL)
+        ms_r = max_over_ranks(ctx.timer_stop())
+        b_reorth = 2 * (8.0 * gi.n_local * k * (k + 1) + 16.0 * gi.n_local * k)     # CGS applied twice
+        detail["full_reorth"] = {"lanczos_ms": ms_r, "iters_per_s": k / (ms_r * 1e-3), "scheme": "CGS2 every step",
+                                 "reorth_algorithmic_gb": b_reorth / 1e9,
+                                 "reorth_gbs": b_reorth / max((ms_r - tm.lanczos_ms) * 1e-3, 1e-9) / 1e9}
+
+    # end to end through the reference-facing call with HOST buffers (pinned), H2D of x and D2H of the answer inside
+    x_host = torch.ones(n, dtype=torch.float64).pin_memory().numpy()
+    y_host = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+    for _ in range(2):
+        ctx.expv_host(x_host, k, out=y_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.expv_host(x_host, k, out=y_host)       # synchronous: returns after the D2H copy of the answer
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": k * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+           "ms_per_step": 1e3 * e2e_s / args.steps, "call": "lz_expv_host (pinned host x -> pinned host e^A x)"}
+    finite = bool(np.isfinite(y_host).all())
+
+    # CPU baseline: the reference's own serial Lanczos on the same graph, bounded sample, rank 0, N == 1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        csr_path = os.path.join(tempfile.gettempdir(), f"lz_bench_{args.workload}_{os.getpid()}.bin")
+        ro, ci = ctx.csr_download()
+        lz.write_bin(csr_path, ro, ci)
+        del ro, ci
+        m = sample_iters_for(nnz)
+        vals, secs, kind = cpu_reference_sample(orc, csr_path, n, nnz, m, reps=1)
+        os.unlink(csr_path)
+        cpu = {"value": vals[0], "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"{m} Lanczos steps of {w['name']} (reference lanczosDecomp<double>, cuda=false, single thread), {secs[0]:.1f} s",
+               "host_cores_available": os.cpu_count()}
+    ctx.close()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["name"], "n": n, "nnz": nnz, "k": k, "reorth": "none", "x": "ones",
+                           "l2_policy": "inputs larger than L2 (CSR %.2f GB + basis %.2f GB per GPU)" % (
+                               (4.0 * gi.nnz_local + 4 * gi.n_local) / 1e9, 8.0 * gi.n_local * k / 1e9),
+                           "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "result_finite": finite, "detail": detail}
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

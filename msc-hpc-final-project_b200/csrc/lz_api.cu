@@ -1,0 +1,464 @@
+// lz_api.cu — C ABI entry points (include/lz.h): context, start vector, the Lanczos driver loop, tridiagonal solve,
+// multOut, read-back, test hooks and timing. Host orchestration only; kernels are in lz_kernels.cu.
+//
+// The driver loop replaces lanczosDecomp<T>::cu_decompose (reference parallel-final/lib/cu_lanczos.cu:97-128), which
+// issues 8 launches + one D2H copy of q_j per step on three streams. Here one step is 3 launches (2 on the last step),
+// the basis never leaves HBM, and multi-GPU steps add one in-place ncclAllGather + two scalar ncclAllReduce.
+#include "lz_ctx.h"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <new>
+#include <string.h>
+
+const lz_nccl_api* lz_nccl() {
+  static lz_nccl_api api;
+  static int state = 0;   // 0 untried, 1 ok, -1 failed
+  if (state == 1) return &api;
+  if (state == -1) { lz_fail(LZ_ERR_NCCL, "libnccl.so.2 could not be loaded"); return nullptr; }
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // share a copy that is already in the process
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!h) { state = -1; lz_fail(LZ_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror()); return nullptr; }
+  bool ok = true;
+  auto sym = [&](const char* name) { void* p = dlsym(h, name); if (!p) ok = false; return p; };
+  api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+  api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+  api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+  if (!ok) { state = -1; lz_fail(LZ_ERR_NCCL, "libnccl.so.2 lacks a required symbol"); return nullptr; }
+  state = 1;
+  return &api;
+}
+
+namespace {
+
+int set_dev(lz_ctx* c) {
+  LZ_CUDA(cudaSetDevice(c->device));
+  return LZ_OK;
+}
+
+void free_vectors(lz_ctx* c) {
+  cudaFree(c->V); cudaFree(c->w); cudaFree(c->xfull); cudaFree(c->xstage); cudaFree(c->ans);
+  cudaFree(c->alpha); cudaFree(c->beta); cudaFree(c->hcoef); cudaFree(c->eigvals); cudaFree(c->eigvecs); cudaFree(c->eigwork);
+  cudaFree(c->coef);
+  c->V = c->w = c->xfull = c->xstage = c->ans = c->alpha = c->beta = c->hcoef = c->eigvals = c->eigvecs = c->eigwork = c->coef = nullptr;
+  c->k_cap = 0;
+  c->have_x = c->have_tridiag = c->have_coef = c->have_ans = false;
+}
+
+// Vectors that depend only on the graph size.
+int ensure_graph_vectors(lz_ctx* c) {
+  if (!c->row_ptr) return lz_fail(LZ_ERR_ARG, "no graph loaded (call lz_csr_upload or lz_graph_generate first)");
+  const uint64_t ldv = (c->n_loc + 31) & ~31ull;
+  if (c->w && c->ldv == ldv && c->vec_n == c->n && c->vec_nloc == c->n_loc) return LZ_OK;
+  free_vectors(c);
+  c->ldv = ldv; c->vec_n = c->n; c->vec_nloc = c->n_loc;
+  LZ_CUDA(cudaMalloc((void**)&c->w, ldv * 8));
+  LZ_CUDA(cudaMalloc((void**)&c->ans, ldv * 8));
+  LZ_CUDA(cudaMalloc((void**)&c->xstage, c->n * 8));
+  LZ_CUDA(cudaMalloc((void**)&c->xfull, c->n_loc * (uint64_t)c->world * 8));
+  LZ_CUDA(cudaMemsetAsync(c->w, 0, ldv * 8, c->stream));
+  LZ_CUDA(cudaMemsetAsync(c->ans, 0, ldv * 8, c->stream));
+  return LZ_OK;
+}
+
+// Basis and k-sized arrays. Growing keeps row 0 (the start vector).
+int ensure_k(lz_ctx* c, uint32_t k) {
+  LZ_TRY(ensure_graph_vectors(c));
+  if (k <= c->k_cap) return LZ_OK;
+  double* nv = nullptr;
+  LZ_CUDA(cudaStreamSynchronize(c->stream));
+  if (cudaMalloc((void**)&nv, (uint64_t)k * c->ldv * 8) != cudaSuccess) {
+    cudaGetLastError();
+    return lz_fail(LZ_ERR_ALLOC, "cannot allocate the Lanczos basis: %u x %llu doubles", k, (unsigned long long)c->ldv);
+  }
+  LZ_CUDA(cudaMemsetAsync(nv, 0, (uint64_t)k * c->ldv * 8, c->stream));
+  if (c->V && c->have_x) LZ_CUDA(cudaMemcpyAsync(nv, c->V, c->ldv * 8, cudaMemcpyDeviceToDevice, c->stream));
+  LZ_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(c->V);
+  c->V = nv;
+  cudaFree(c->alpha); cudaFree(c->beta); cudaFree(c->hcoef); cudaFree(c->eigvals); cudaFree(c->eigvecs); cudaFree(c->eigwork); cudaFree(c->coef);
+  LZ_CUDA(cudaMalloc((void**)&c->alpha, k * 8)); LZ_CUDA(cudaMalloc((void**)&c->beta, k * 8));
+  LZ_CUDA(cudaMalloc((void**)&c->hcoef, k * 8)); LZ_CUDA(cudaMalloc((void**)&c->eigvals, k * 8));
+  LZ_CUDA(cudaMalloc((void**)&c->eigvecs, (uint64_t)k * k * 8)); LZ_CUDA(cudaMalloc((void**)&c->eigwork, (uint64_t)k * k * 8));
+  LZ_CUDA(cudaMalloc((void**)&c->coef, k * 8));
+  c->k_cap = k;
+  c->have_tridiag = c->have_coef = c->have_ans = false;
+  return LZ_OK;
+}
+
+cudaEvent_t next_event(lz_ctx* c) {
+  if (c->ev_used == c->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->ev_pool.push_back(e);
+  }
+  return c->ev_pool[c->ev_used++];
+}
+// profiling marks: kind 0 spmv, 1 update/scale, 2 comm, 3 reorth
+struct Mark { int kind; cudaEvent_t a, b; };
+thread_local std::vector<Mark> g_marks;
+
+struct Scope {
+  lz_ctx* c; int kind; cudaEvent_t a = nullptr;
+  Scope(lz_ctx* c_, int kind_) : c(c_), kind(kind_) {
+    if (c->profiling) { a = next_event(c); cudaEventRecord(a, c->stream); }
+  }
+  ~Scope() {
+    if (c->profiling) { cudaEvent_t b = next_event(c); cudaEventRecord(b, c->stream); g_marks.push_back({kind, a, b}); }
+  }
+};
+
+int allreduce_sum(lz_ctx* c, double* buf, size_t count) {
+  if (c->world == 1) return LZ_OK;
+  Scope s(c, 2);
+  LZ_NCCL(lz_nccl()->AllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->stream));
+  return LZ_OK;
+}
+int allgather_inplace(lz_ctx* c, double* full) {
+  if (c->world == 1) return LZ_OK;
+  Scope s(c, 2);
+  LZ_NCCL(lz_nccl()->AllGather(full + (uint64_t)c->rank * c->n_loc, full, c->n_loc, ncclDouble, c->comm, c->stream));
+  return LZ_OK;
+}
+
+}  // namespace
+
+extern "C" int lz_device_count(int* count_out) {
+  if (!count_out) return lz_fail(LZ_ERR_ARG, "null argument");
+  LZ_CUDA(cudaGetDeviceCount(count_out));
+  return LZ_OK;
+}
+
+static int create_common(int device, int rank, int world, const void* uid, lz_ctx** out) {
+  if (!out) return lz_fail(LZ_ERR_ARG, "null ctx_out");
+  if (world < 1 || rank < 0 || rank >= world) return lz_fail(LZ_ERR_ARG, "bad rank %d / world %d", rank, world);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return lz_fail(LZ_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+  if (device < 0 || device >= ndev) return lz_fail(LZ_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+  LZ_CUDA(cudaSetDevice(device));
+  lz_ctx* c = new (std::nothrow) lz_ctx();
+  if (!c) return lz_fail(LZ_ERR_ALLOC, "out of host memory");
+  c->device = device; c->rank = rank; c->world = world;
+  cudaDeviceProp prop;
+  LZ_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  LZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  LZ_CUDA(cudaEventCreate(&c->ev_a)); LZ_CUDA(cudaEventCreate(&c->ev_b));
+  LZ_CUDA(cudaEventCreate(&c->ev_e0)); LZ_CUDA(cudaEventCreate(&c->ev_e1));
+  LZ_CUDA(cudaEventCreate(&c->ev_m0)); LZ_CUDA(cudaEventCreate(&c->ev_m1));
+  LZ_CUDA(cudaEventCreate(&c->ev_t0)); LZ_CUDA(cudaEventCreate(&c->ev_t1));
+  LZ_CUDA(cudaMalloc((void**)&c->scal, 16 * 8));
+  LZ_CUDA(cudaMemset(c->scal, 0, 16 * 8));
+  LZ_CUDA(cudaMalloc((void**)&c->ticket, 16 * sizeof(unsigned int)));
+  LZ_CUDA(cudaMemset(c->ticket, 0, 16 * sizeof(unsigned int)));
+  LZ_CUDA(cudaMalloc((void**)&c->status, sizeof(int)));
+  LZ_CUDA(cudaMemset(c->status, 0, sizeof(int)));
+  if (world > 1) {
+    if (!uid) return lz_fail(LZ_ERR_ARG, "world > 1 needs an NCCL unique id");
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == LZ_NCCL_UID_BYTES, "NCCL unique id size");
+    memcpy(&id, uid, sizeof(id));
+    if (!lz_nccl()) return LZ_ERR_NCCL;
+    LZ_NCCL(lz_nccl()->CommInitRank(&c->comm, world, id, rank));
+  }
+  *out = c;
+  return LZ_OK;
+}
+
+extern "C" int lz_create(int device, lz_ctx** ctx_out) { return create_common(device, 0, 1, nullptr, ctx_out); }
+
+extern "C" int lz_nccl_unique_id(void* uid_out) {
+  if (!uid_out) return lz_fail(LZ_ERR_ARG, "null argument");
+  ncclUniqueId id;
+  if (!lz_nccl()) return LZ_ERR_NCCL;
+  LZ_NCCL(lz_nccl()->GetUniqueId(&id));
+  memcpy(uid_out, &id, sizeof(id));
+  return LZ_OK;
+}
+
+extern "C" int lz_create_dist(int device, int rank, int world, const void* uid, lz_ctx** ctx_out) {
+  return create_common(device, rank, world, uid, ctx_out);
+}
+
+extern "C" int lz_destroy(lz_ctx* c) {
+  if (!c) return LZ_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->comm && lz_nccl()) lz_nccl()->CommDestroy(c->comm);
+  free_vectors(c);
+  lz_free_graph(c);
+  cudaFree(c->scal); cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->status); cudaFree(c->flush_buf);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_e0); cudaEventDestroy(c->ev_e1);
+  cudaEventDestroy(c->ev_m0); cudaEventDestroy(c->ev_m1); cudaEventDestroy(c->ev_t0); cudaEventDestroy(c->ev_t1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return LZ_OK;
+}
+
+extern "C" int lz_sync(lz_ctx* c) {
+  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  LZ_TRY(set_dev(c));
+  LZ_CUDA(cudaStreamSynchronize(c->stream));
+  return LZ_OK;
+}
+
+extern "C" int lz_set_spmv_variant(lz_ctx* c, int variant) {
+  if (!c || variant < 0 || variant > LZ_SPMV_WARP) return lz_fail(LZ_ERR_ARG, "bad SpMV variant");
+  c->spmv_variant = variant;
+  c->plan = (variant == LZ_SPMV_WARP) ? c->plan_warp : c->plan_auto;
+  return LZ_OK;
+}
+
+// x -> device, ||x||^2 -> scal[2], q_0 = x/||x|| -> V[0] (and the gathered buffer when world > 1).
+// Replaces cu_lanczos.cu:30-34 (host normalisation) + :88 (H2D of q_0).
+extern "C" int lz_set_start_vector(lz_ctx* c, const double* x_host) {
+  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  LZ_TRY(set_dev(c));
+  LZ_TRY(ensure_k(c, c->k_cap ? c->k_cap : 2));
+  if (x_host) {
+    LZ_CUDA(cudaMemcpyAsync(c->xstage, x_host, c->n * 8, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    LZ_TRY(lz_k_fill(c, c->xstage, c->n, 1.0));   // all ones, as every reference driver uses (main.cu:79)
+  }
+  LZ_TRY(lz_k_norm2(c, c->xstage, c->n, c->scal + 2));
+  if (c->world > 1) {
+    LZ_TRY(lz_k_permute_in(c, c->xstage, c->scal + 2, 0, c->n_loc * (uint64_t)c->world, c->xfull));
+    LZ_CUDA(cudaMemcpyAsync(c->V, c->xfull + (uint64_t)c->rank * c->n_loc, c->n_loc * 8, cudaMemcpyDeviceToDevice, c->stream));
+  } else {
+    LZ_TRY(lz_k_permute_in(c, c->xstage, c->scal + 2, 0, c->n_loc, c->V));
+  }
+  c->have_x = true;
+  c->have_tridiag = c->have_coef = c->have_ans = false;
+  return LZ_OK;
+}
+
+extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
+  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  if (k < 1) return lz_fail(LZ_ERR_ARG, "krylov dimension must be >= 1");
+  if (reorth != LZ_REORTH_NONE && reorth != LZ_REORTH_FULL) return lz_fail(LZ_ERR_ARG, "bad reorth mode %d", reorth);
+  if (!c->have_x) return lz_fail(LZ_ERR_ARG, "lz_set_start_vector must be called before lz_lanczos_run");
+  LZ_TRY(set_dev(c));
+  LZ_TRY(ensure_k(c, k));
+  const uint64_t ldv = c->ldv;
+  const bool dist = c->world > 1;
+  c->ev_used = 0;
+  g_marks.clear();
+  LZ_CUDA(cudaEventRecord(c->ev_a, c->stream));
+  if (dist) {   // q_0 into the gathered buffer (a previous run left q_{k-1} there)
+    LZ_CUDA(cudaMemcpyAsync(c->xfull + (uint64_t)c->rank * c->n_loc, c->V, c->n_loc * 8, cudaMemcpyDeviceToDevice, c->stream));
+    LZ_TRY(allgather_inplace(c, c->xfull));
+  }
+  for (uint32_t j = 0; j < k; j++) {
+    double* qj = c->V + (uint64_t)j * ldv;
+    {  // w = A q_j ; alpha_j = w . q_j                                   (cu_lanczos.cu:101-105)
+      Scope s(c, 0);
+      LZ_TRY(lz_k_spmv_dot(c, dist ? c->xfull : qj, qj, c->w, c->alpha + j));
+    }
+    LZ_TRY(allreduce_sum(c, c->alpha + j, 1));
+    if (j + 1 == k) break;                                               // last step needs alpha only (cu_lanczos.cu:116)
+    {  // w -= alpha_j q_j ; w -= beta_{j-1} q_{j-1} ; ||w||^2             (cu_lanczos.cu:108-120)
+      Scope s(c, 1);
+      LZ_TRY(lz_k_update_norm(c, c->w, qj, j ? qj - ldv : nullptr, c->alpha + j, j ? c->beta + (j - 1) : nullptr,
+                              reorth ? nullptr : c->scal + 1));
+    }
+    if (reorth) {  // classical Gram-Schmidt, twice, against q_0..q_j
+      Scope s(c, 3);
+      for (int pass = 0; pass < 2; pass++) {
+        LZ_TRY(lz_k_multidot(c, c->V, j + 1, c->w, c->hcoef));
+        LZ_TRY(allreduce_sum(c, c->hcoef, j + 1));
+        LZ_TRY(lz_k_combine(c, c->V, j + 1, c->hcoef, -1.0, c->w, c->w, pass == 1 ? c->scal + 1 : nullptr));
+      }
+    }
+    LZ_TRY(allreduce_sum(c, c->scal + 1, 1));
+    {  // beta_j = ||w|| ; q_{j+1} = w / beta_j                            (cu_lanczos.cu:120-123)
+      Scope s(c, 1);
+      LZ_TRY(lz_k_scale(c, c->w, c->scal + 1, qj + ldv, dist ? c->xfull + (uint64_t)c->rank * c->n_loc : nullptr, c->beta + j));
+    }
+    LZ_TRY(allgather_inplace(c, c->xfull));
+  }
+  LZ_CUDA(cudaEventRecord(c->ev_b, c->stream));
+  c->k_done = k;
+  c->reorth_done = reorth;
+  c->have_tridiag = true;
+  c->have_coef = c->have_ans = false;
+  c->tm.spmv_launches = k;
+  return LZ_OK;
+}
+
+extern "C" int lz_get_tridiag(lz_ctx* c, double* alpha_out, double* beta_out) {
+  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  if (!c->have_tridiag) return lz_fail(LZ_ERR_ARG, "no decomposition available");
+  LZ_TRY(set_dev(c));
+  if (alpha_out) LZ_CUDA(cudaMemcpyAsync(alpha_out, c->alpha, c->k_done * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (beta_out && c->k_done > 1) LZ_CUDA(cudaMemcpyAsync(beta_out, c->beta, (c->k_done - 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  LZ_CUDA(cudaStreamSynchronize(c->stream));
+  if (alpha_out)
+    for (uint32_t i = 0; i < c->k_done; i++)
+      if (!isfinite(alpha_out[i])) return lz_fail(LZ_ERR_NUMERIC, "alpha[%u] is not finite (Lanczos breakdown: a beta was 0)", i);
+  return LZ_OK;
+}
+
+extern "C" int lz_tridiag_expv(lz_ctx* c) {
+  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  if (!c->have_tridiag) return lz_fail(LZ_ERR_ARG, "lz_lanczos_run must be called before lz_tridiag_expv");
+  LZ_TRY(set_dev(c));
+  LZ_CUDA(cudaEventRecord(c->ev_e0, c->stream));
+  LZ_TRY(lz_k_tridiag_expv(c, c->k_done));
+  LZ_CUDA(cudaEventRecord(c->ev_e1, c->stream));
+  c->have_coef = true;
+  c->have_ans = false;
+  return LZ_OK;
+}
+
+extern "C" int lz_get_eigen(lz_ctx* c, double* eigvals_out, double* eigvecs_out, double* coeff_out) {
+  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  if (!c->have_coef) return lz_fail(LZ_ERR_ARG, "lz_tridiag_expv must be called first");
+  LZ_TRY(set_dev(c));
+  const uint32_t k = c->k_done;
+  int st = 0;
+  if (eigvals_out) LZ_CUDA(cudaMemcpyAsync(eigvals_out, c->eigvals, k * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (eigvecs_out) LZ_CUDA(cudaMemcpyAsync(eigvecs_out, c->eigvecs, (uint64_t)k * k * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (coeff_out) LZ_CUDA(cudaMemcpyAsync(coeff_out, c->coef, k * 8, cudaMemcpyDeviceToHost, c->stream));
+  LZ_CUDA(cudaMemcpyAsync(&st, c->status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  LZ_CUDA(cudaStreamSynchronize(c->stream));
+  if (st & 0x3FFFFFFF) return lz_fail(LZ_ERR_NUMERIC, "tridiagonal eigensolver: eigenvalue %d did not converge", (st & 0x3FFFFFFF) - 1);
+  if (st & 0x40000000) return lz_fail(LZ_ERR_NUMERIC, "coefficient vector is not finite (exp of a Ritz value overflowed, or breakdown)");
+  return LZ_OK;
+}
+
+extern "C" int lz_multout(lz_ctx* c) {
+  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  if (!c->have_coef) return lz_fail(LZ_ERR_ARG, "lz_tridiag_expv must be called before lz_multout");
+  LZ_TRY(set_dev(c));
+  LZ_CUDA(cudaEventRecord(c->ev_m0, c->stream));
+  LZ_TRY(lz_k_combine(c, c->V, c->k_done, c->coef, 1.0, nullptr, c->ans, nullptr));
+  LZ_CUDA(cudaEventRecord(c->ev_m1, c->stream));
+  c->have_ans = true;
+  return LZ_OK;
+}
+
+static int gather_to_host(lz_ctx* c, const double* local, double* host_out) {
+  // local [n_loc] (new order, this rank's slice) -> host [n] original order, on every rank
+  const double* full = local;
+  if (c->world > 1) {
+    LZ_CUDA(cudaMemcpyAsync(c->xfull + (uint64_t)c->rank * c->n_loc, local, c->n_loc * 8, cudaMemcpyDeviceToDevice, c->stream));
+    LZ_NCCL(lz_nccl()->AllGather(c->xfull + (uint64_t)c->rank * c->n_loc, c->xfull, c->n_loc, ncclDouble, c->comm, c->stream));
+    full = c->xfull;
+  }
+  LZ_TRY(lz_k_permute_out(c, full, c->xstage));
+  LZ_CUDA(cudaMemcpyAsync(host_out, c->xstage, c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+  LZ_CUDA(cudaStreamSynchronize(c->stream));
+  return LZ_OK;
+}
+
+extern "C" int lz_get_ans(lz_ctx* c, double* ans_host) {
+  if (!c || !ans_host) return lz_fail(LZ_ERR_ARG, "null argument");
+  if (!c->have_ans) return lz_fail(LZ_ERR_ARG, "lz_multout must be called before lz_get_ans");
+  LZ_TRY(set_dev(c));
+  return gather_to_host(c, c->ans, ans_host);
+}
+
+extern "C" int lz_expv_host(lz_ctx* c, const double* x_host, uint32_t k, int reorth, double* ans_host) {
+  LZ_TRY(lz_set_start_vector(c, x_host));
+  LZ_TRY(lz_lanczos_run(c, k, reorth));
+  LZ_TRY(lz_tridiag_expv(c));
+  LZ_TRY(lz_multout(c));
+  LZ_TRY(lz_get_ans(c, ans_host));
+  int st = 0;
+  LZ_CUDA(cudaMemcpy(&st, c->status, sizeof(int), cudaMemcpyDeviceToHost));
+  if (st & 0x3FFFFFFF) return lz_fail(LZ_ERR_NUMERIC, "tridiagonal eigensolver: eigenvalue %d did not converge", (st & 0x3FFFFFFF) - 1);
+  if (st & 0x40000000) return lz_fail(LZ_ERR_NUMERIC, "result is not finite (exp of a Ritz value overflowed, or Lanczos breakdown)");
+  return LZ_OK;
+}
+
+extern "C" int lz_spmv_host(lz_ctx* c, const double* x_host, double* y_host) {
+  if (!c || !x_host || !y_host) return lz_fail(LZ_ERR_ARG, "null argument");
+  LZ_TRY(set_dev(c));
+  LZ_TRY(ensure_graph_vectors(c));
+  const uint64_t n_pad = c->n_loc * (uint64_t)c->world;
+  double *xg = nullptr, *y = nullptr, *dummy = nullptr;
+  LZ_CUDA(cudaMalloc((void**)&xg, n_pad * 8));
+  LZ_CUDA(cudaMalloc((void**)&y, c->ldv * 8));
+  LZ_CUDA(cudaMalloc((void**)&dummy, 8));
+  int rc = LZ_OK;
+  do {
+    if (cudaMemcpyAsync(c->xstage, x_host, c->n * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = lz_fail(LZ_ERR_CUDA, "H2D failed"); break; }
+    if ((rc = lz_k_permute_in(c, c->xstage, nullptr, 0, n_pad, xg)) != LZ_OK) break;
+    if ((rc = lz_k_spmv_dot(c, xg, xg + (uint64_t)c->rank * c->n_loc, y, dummy)) != LZ_OK) break;
+    rc = gather_to_host(c, y, y_host);
+  } while (0);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(xg); cudaFree(y); cudaFree(dummy);
+  return rc;
+}
+
+extern "C" int lz_get_basis(lz_ctx* c, uint32_t j, double* q_host) {
+  if (!c || !q_host) return lz_fail(LZ_ERR_ARG, "null argument");
+  if (!c->have_x || j >= (c->have_tridiag ? c->k_done : 1u)) return lz_fail(LZ_ERR_ARG, "basis vector %u not available", j);
+  LZ_TRY(set_dev(c));
+  return gather_to_host(c, c->V + (uint64_t)j * c->ldv, q_host);
+}
+
+extern "C" int lz_set_profiling(lz_ctx* c, int on) {
+  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  c->profiling = on != 0;
+  return LZ_OK;
+}
+
+extern "C" int lz_timings_get(lz_ctx* c, lz_timings* out) {
+  if (!c || !out) return lz_fail(LZ_ERR_ARG, "null argument");
+  LZ_TRY(set_dev(c));
+  LZ_CUDA(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  if (c->have_tridiag && cudaEventElapsedTime(&ms, c->ev_a, c->ev_b) == cudaSuccess) c->tm.lanczos_ms = ms;
+  if (c->have_coef && cudaEventElapsedTime(&ms, c->ev_e0, c->ev_e1) == cudaSuccess) c->tm.tridiag_ms = ms;
+  if (c->have_ans && cudaEventElapsedTime(&ms, c->ev_m0, c->ev_m1) == cudaSuccess) c->tm.multout_ms = ms;
+  double sum[4] = {0, 0, 0, 0};
+  int cnt[4] = {0, 0, 0, 0};
+  for (const Mark& m : g_marks) {
+    if (cudaEventElapsedTime(&ms, m.a, m.b) == cudaSuccess) { sum[m.kind] += ms; cnt[m.kind]++; }
+  }
+  cudaGetLastError();
+  const uint32_t steps = c->k_done ? c->k_done : 1;
+  c->tm.spmv_ms_avg = cnt[0] ? (float)(sum[0] / cnt[0]) : 0.f;
+  c->tm.update_ms_avg = (float)(sum[1] / steps);
+  c->tm.comm_ms_avg = (float)(sum[2] / steps);
+  c->tm.reorth_ms_total = (float)sum[3];
+  c->tm.kernel_launches = c->launches;
+  *out = c->tm;
+  return LZ_OK;
+}
+
+extern "C" int lz_timer_start(lz_ctx* c) {
+  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  LZ_TRY(set_dev(c));
+  LZ_CUDA(cudaEventRecord(c->ev_t0, c->stream));
+  return LZ_OK;
+}
+extern "C" int lz_timer_stop(lz_ctx* c, float* ms_out) {
+  if (!c || !ms_out) return lz_fail(LZ_ERR_ARG, "null argument");
+  LZ_TRY(set_dev(c));
+  LZ_CUDA(cudaEventRecord(c->ev_t1, c->stream));
+  LZ_CUDA(cudaEventSynchronize(c->ev_t1));
+  LZ_CUDA(cudaEventElapsedTime(ms_out, c->ev_t0, c->ev_t1));
+  return LZ_OK;
+}
+
+extern "C" int lz_flush_l2(lz_ctx* c) {
+  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  LZ_TRY(set_dev(c));
+  if (!c->flush_buf) {
+    c->flush_bytes = 512ull << 20;   // 4x the 126 MB L2
+    LZ_CUDA(cudaMalloc(&c->flush_buf, c->flush_bytes));
+  }
+  LZ_CUDA(cudaMemsetAsync(c->flush_buf, 0, c->flush_bytes, c->stream));
+  return LZ_OK;
+}

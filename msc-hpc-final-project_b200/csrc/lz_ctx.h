@@ -1,0 +1,129 @@
+// lz_ctx.h — the per-GPU context behind the C ABI (include/lz.h) and the launch interfaces between translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <vector>
+#include "lz_internal.h"
+
+#define LZ_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return lz_fail(LZ_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+// NCCL is bound at run time (dlopen) so that (a) single-GPU use needs no NCCL at all and (b) inside a process that
+// already loaded a libnccl.so.2 (e.g. PyTorch's bundled one) we share that copy instead of clashing with it.
+struct lz_nccl_api {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(ncclResult_t);
+  ncclResult_t (*GetVersion)(int*);
+};
+const lz_nccl_api* lz_nccl();   // nullptr (with lz_last_error set) when no libnccl.so.2 can be loaded
+#define LZ_NCCL(call)                                                                                   \
+  do {                                                                                                  \
+    ncclResult_t r_ = (call);                                                                           \
+    if (r_ != ncclSuccess)                                                                              \
+      return lz_fail(LZ_ERR_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call, lz_nccl()->GetErrorString(r_)); \
+  } while (0)
+#define LZ_TRY(call)            \
+  do {                          \
+    int rc_ = (call);           \
+    if (rc_ != LZ_OK) return rc_; \
+  } while (0)
+
+// SpMV launch plan: local rows are sorted by length (non-increasing), so each bin is a contiguous row range that one
+// kernel variant (lanes-per-row = 1 << log2_lanes) serves.
+#define LZ_MAX_BINS 8
+struct lz_spmv_bin {
+  uint32_t row_begin, row_end;   // local rows [begin, end)
+  uint32_t log2_lanes;           // lanes cooperating on one row
+  uint32_t block_begin;          // first CTA of this bin in the fused launch
+};
+struct lz_spmv_plan {
+  lz_spmv_bin bin[LZ_MAX_BINS];
+  uint32_t nbins;
+  uint32_t nblocks;
+};
+
+struct lz_ctx {
+  int device = 0, rank = 0, world = 1;
+  int sm_count = 148;
+  ncclComm_t comm = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;      // lz_lanczos_run
+  cudaEvent_t ev_e0 = nullptr, ev_e1 = nullptr;    // lz_tridiag_expv
+  cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;    // lz_multout
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;    // lz_timer_start / lz_timer_stop
+
+  // ---- graph ------------------------------------------------------------------------------------------------------
+  uint64_t n = 0, nnz = 0;         // global
+  uint64_t n_loc = 0;              // rows per rank = ceil(n / world); global padded length = n_loc * world
+  uint64_t nnz_loc = 0;
+  uint64_t ldv = 0;                // leading dimension of V (n_loc rounded up to 32 doubles => 256-byte aligned rows)
+  uint32_t max_degree = 0;
+  uint64_t empty_rows = 0;
+  uint32_t* orig_ro = nullptr;     // device, original-order full CSR (kept for lz_csr_download)
+  uint32_t* orig_ci = nullptr;
+  uint32_t* row_ptr = nullptr;     // device, local rows, [n_loc + 1]
+  uint32_t* col = nullptr;         // device, [nnz_loc], NEW global column ids, ascending within a row
+  uint32_t* new2old = nullptr;     // device, [n_loc * world]; 0xFFFFFFFF for padding slots
+  lz_spmv_plan plan_auto{}, plan_warp{}, plan{};
+  int spmv_variant = LZ_SPMV_AUTO;
+
+  // ---- vectors ----------------------------------------------------------------------------------------------------
+  uint64_t vec_n = 0, vec_nloc = 0; // graph size the vectors below were allocated for
+  uint32_t k_cap = 0;              // rows allocated in V
+  uint32_t k_done = 0;             // steps of the last run
+  int reorth_done = 0;
+  double* V = nullptr;             // device, [k_cap][ldv] basis, vector-contiguous (parallel-mult-on-card layout)
+  double* w = nullptr;             // device, [n_loc]
+  double* xfull = nullptr;         // device, [n_loc * world] gathered Krylov vector (world > 1), else unused
+  double* xstage = nullptr;        // device, [n] staging for host vectors in original order
+  double* ans = nullptr;           // device, [n_loc]
+  double* alpha = nullptr;         // device, [k_cap]
+  double* beta = nullptr;          // device, [k_cap]
+  double* scal = nullptr;          // device scalars: [0]=alpha acc, [1]=norm2 acc, [2]=x_norm, [3..] spare
+  double* partials = nullptr;      // device, per-CTA partial sums
+  uint32_t partials_cap = 0;
+  unsigned int* ticket = nullptr;  // device, last-block counters
+  double* hcoef = nullptr;         // device, [k_cap] reorth coefficients / multOut coefficients
+  double* eigvals = nullptr;       // device, [k_cap]
+  double* eigvecs = nullptr;       // device, [k_cap * k_cap] (row-major, dstevd layout), + scratch of same size
+  double* eigwork = nullptr;
+  double* coef = nullptr;          // device, [k_cap]
+  int* status = nullptr;           // device, eigensolver status
+  bool have_x = false, have_tridiag = false, have_coef = false, have_ans = false;
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+
+  // ---- measurement ------------------------------------------------------------------------------------------------
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  lz_timings tm{};
+  uint32_t launches = 0;
+};
+
+// lz_graph.cu
+int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, uint32_t* ci_d);  // takes ownership of ro_d / ci_d
+void lz_free_graph(lz_ctx* c);
+
+// lz_kernels.cu — all launches are asynchronous on c->stream
+int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out /* device scalar or null */);
+int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev, const double* alpha, const double* beta_prev,
+                     double* norm2_out /* device scalar or null */);
+int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* q_next_copy, double* beta_out);
+int lz_k_norm2(lz_ctx* c, const double* v, uint64_t len, double* out);
+int lz_k_multidot(lz_ctx* c, const double* V, uint32_t nvec, const double* w, double* h_out /* device [nvec] */);
+int lz_k_combine(lz_ctx* c, const double* V, uint32_t nvec, const double* coef, double coef_sign, const double* base, double* out,
+                 double* norm2_out /* device scalar or null */);
+int lz_k_tridiag_expv(lz_ctx* c, uint32_t k);
+// dst[i] = x_orig[new2old[first + i]] (/ sqrt(*norm2) when norm2 != null), i < count; padding slots -> 0
+int lz_k_permute_in(lz_ctx* c, const double* x_orig, const double* norm2, uint64_t first, uint64_t count, double* dst);
+int lz_k_permute_out(lz_ctx* c, const double* y_new_full, double* y_orig);
+int lz_k_fill(lz_ctx* c, double* p, uint64_t n, double value);

@@ -1,0 +1,573 @@
+// lz_kernels.cu — hand-written sm_100a kernels of the Lanczos e^A·x hot path. Every kernel is HBM/L2-bandwidth bound
+// fp64 streaming or gather work (<= 0.25 flop/byte): no tensor-core shapes anywhere.
+//
+//   k_spmv_dot      w = A x  (value-less CSR gather-sum) fused with the partial of alpha = w . q_j
+//                   replaces cu_spMV1 + cu_dot_prod + cu_reduce (reference parallel-final/lib/cu_SPMV.cu:31-41,
+//                   cu_linalg.cu:67-131; launches at cu_lanczos.cu:101-105)
+//   k_update_norm   w -= alpha q_j ; w -= beta_{j-1} q_{j-1} ; partial of ||w||^2          (one pass)
+//                   replaces cu_dpax x2 + cu_norm_sq + cu_reduce_sqrt (cu_linalg.cu:223-226,184-208,146-170; cu_lanczos.cu:108-120)
+//   k_scale         q_{j+1} = w / beta_j  written straight into the resident basis (and the all-gather slot)
+//                   replaces cu_dvexda (cu_linalg.cu:241-244; cu_lanczos.cu:123) and the per-step D2H of q_j (:126)
+//   k_multidot      h = V_j^T w   (tall-skinny GEMV-T) for full reorthogonalisation (precedent: serial/lib/lanczos.cc:85-91)
+//   k_combine       out = base + s * V^T-combination: reorth update  w -= V h  and  multOut  ans = V c
+//                   replaces cblas_dgemv / cublasDgemv (multiplyOut.cu:43-47, parallel-mult-on-card/lib/cu_multiplyOut.cu:66-72)
+//   k_tridiag_expv  eigen-decomposition of the k x k tridiagonal (implicit-shift QL) + c = ||x|| Z (e^lambda . Z^T e1)
+//                   replaces LAPACKE_dstevd (eigen.cu:17-21) and multiplyOut.cu:30-40
+//
+// All grid-wide reductions are deterministic: per-CTA partials in a fixed slot, summed in a fixed order by the last CTA
+// to finish (ticket counter), result left in device memory so the next kernel reads it without a host round-trip —
+// the same "scalars never visit the host" property as the reference (cu_linalg.cu:223-226 take T* device scalars).
+#include "lz_ctx.h"
+
+#include <math.h>
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the CTA; result valid in thread 0. `sm` has kWarps doubles.
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();   // protect sm from a previous use
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    v = (lane < kWarps) ? sm[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+// Deterministic grid reduction tail. Thread 0 of every CTA passes its CTA value; the last CTA to arrive sums all
+// `gridDim.x` partials in index order (strided per thread, then a fixed tree) and stores op(sum) to *out.
+__device__ __forceinline__ void grid_sum_finish(double cta_val, double* partials, unsigned int* ticket, double* out, double* sm,
+                                                bool* s_last) {
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = cta_val;
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    *s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (*s_last) {
+    __threadfence();
+    double acc = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) acc += __ldcg(partials + i);
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) {
+      *out = acc;
+      *ticket = 0u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------- SpMV
+// One row is served by L = 2^LG cooperating lanes. Local rows are sorted by length, so all rows of a bin have
+// len in (L, 2L] (or > 32 for L = 32): lanes of a warp run the same trip count and adjacent rows are adjacent in col[].
+template <int LG>
+__device__ __forceinline__ double spmv_rows(const lz_spmv_bin& bin, uint32_t blk, const uint32_t* __restrict__ rp,
+                                            const uint32_t* __restrict__ col, const double* __restrict__ x,
+                                            const double* __restrict__ q, double* __restrict__ w) {
+  constexpr uint32_t L = 1u << LG;
+  const uint32_t t = blk * kBlock + threadIdx.x;
+  const uint32_t row = bin.row_begin + (t >> LG);
+  const uint32_t sub = t & (L - 1);
+  const bool valid = row < bin.row_end;
+  double sum = 0.0;
+  if (valid) {
+    uint32_t j = __ldg(rp + row) + sub;
+    const uint32_t e = __ldg(rp + row + 1);
+    // two independent gather chains per lane
+    double s1 = 0.0;
+    for (; j + L < e; j += 2 * L) {
+      const uint32_t c0 = __ldcs(col + j), c1 = __ldcs(col + j + L);
+      sum += __ldg(x + c0);
+      s1 += __ldg(x + c1);
+    }
+    if (j < e) sum += __ldg(x + __ldcs(col + j));
+    sum += s1;
+  }
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  double d = 0.0;
+  if (valid && sub == 0) {
+    w[row] = sum;
+    d = sum * q[row];
+  }
+  return d;
+}
+
+__global__ void __launch_bounds__(kBlock) k_spmv_dot(const __grid_constant__ lz_spmv_plan plan, const uint32_t* __restrict__ rp,
+                                                     const uint32_t* __restrict__ col, const double* __restrict__ x,
+                                                     const double* __restrict__ q, double* __restrict__ w, double* partials,
+                                                     unsigned int* ticket, double* alpha_out) {
+  __shared__ double sm[kWarps];
+  __shared__ bool s_last;
+  uint32_t b = 0;
+#pragma unroll
+  for (uint32_t i = 1; i < LZ_MAX_BINS; i++)
+    if (i < plan.nbins && blockIdx.x >= plan.bin[i].block_begin) b = i;
+  const lz_spmv_bin& bin = plan.bin[b];
+  const uint32_t blk = blockIdx.x - bin.block_begin;
+  double d;
+  switch (bin.log2_lanes) {
+    case 5: d = spmv_rows<5>(bin, blk, rp, col, x, q, w); break;
+    case 4: d = spmv_rows<4>(bin, blk, rp, col, x, q, w); break;
+    case 3: d = spmv_rows<3>(bin, blk, rp, col, x, q, w); break;
+    case 2: d = spmv_rows<2>(bin, blk, rp, col, x, q, w); break;
+    case 1: d = spmv_rows<1>(bin, blk, rp, col, x, q, w); break;
+    default: d = spmv_rows<0>(bin, blk, rp, col, x, q, w); break;
+  }
+  d = block_sum(d, sm);
+  grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last);
+}
+
+// --------------------------------------------------------------------------------------------- fused vector update
+// w <- (w - alpha q_j) - beta_prev q_prev, partial of ||w||^2. Same operation order as lanczos.cu:36-43.
+__global__ void __launch_bounds__(kBlock) k_update_norm(double* __restrict__ w, const double* __restrict__ qj, const double* __restrict__ qp,
+                                                        const double* __restrict__ alpha_p, const double* __restrict__ beta_p,
+                                                        uint64_t n, double* partials, unsigned int* ticket, double* norm2_out) {
+  __shared__ double sm[kWarps];
+  __shared__ bool s_last;
+  const double a = *alpha_p;
+  const double b = qp ? *beta_p : 0.0;
+  const uint64_t n2 = n >> 1;
+  double acc = 0.0;
+  double2* w2 = reinterpret_cast<double2*>(w);
+  const double2* q2 = reinterpret_cast<const double2*>(qj);
+  const double2* p2 = reinterpret_cast<const double2*>(qp);
+  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
+    double2 wv = w2[i];
+    const double2 qv = q2[i];
+    wv.x -= a * qv.x;
+    wv.y -= a * qv.y;
+    if (qp) {
+      const double2 pv = p2[i];
+      wv.x -= b * pv.x;
+      wv.y -= b * pv.y;
+    }
+    w2[i] = wv;
+    acc += wv.x * wv.x;
+    acc += wv.y * wv.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double t = w[n - 1] - a * qj[n - 1];
+    if (qp) t -= b * qp[n - 1];
+    w[n - 1] = t;
+    acc += t * t;
+  }
+  acc = block_sum(acc, sm);
+  if (norm2_out) grid_sum_finish(acc, partials, ticket, norm2_out, sm, &s_last);
+}
+
+// q_next = w / sqrt(norm2)  (true division, as cu_dvexda); optional second copy into the all-gather buffer; beta_out = sqrt(norm2)
+__global__ void __launch_bounds__(kBlock) k_scale(const double* __restrict__ w, const double* __restrict__ norm2_p, uint64_t n,
+                                                  double* __restrict__ q_next, double* __restrict__ q_copy, double* beta_out) {
+  const double beta = sqrt(*norm2_p);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && beta_out) *beta_out = beta;
+  const uint64_t n2 = n >> 1;
+  const double2* w2 = reinterpret_cast<const double2*>(w);
+  double2* q2 = reinterpret_cast<double2*>(q_next);
+  double2* c2 = reinterpret_cast<double2*>(q_copy);
+  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
+    double2 v = w2[i];
+    v.x /= beta;
+    v.y /= beta;
+    q2[i] = v;
+    if (q_copy) c2[i] = v;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double v = w[n - 1] / beta;
+    q_next[n - 1] = v;
+    if (q_copy) q_copy[n - 1] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_norm2(const double* __restrict__ v, uint64_t n, double* partials, unsigned int* ticket,
+                                                  double* out) {
+  __shared__ double sm[kWarps];
+  __shared__ bool s_last;
+  double acc = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kBlock) acc += v[i] * v[i];
+  acc = block_sum(acc, sm);
+  grid_sum_finish(acc, partials, ticket, out, sm, &s_last);
+}
+
+// dst[i] = x_orig[new2old[first + i]] / sqrt(norm2) for i < count (0 for padding slots)
+__global__ void k_permute_in(const double* __restrict__ x_orig, const uint32_t* __restrict__ new2old, uint64_t first, uint64_t count,
+                             const double* __restrict__ norm2_p, double* __restrict__ dst) {
+  const double nrm = sqrt(*norm2_p);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t o = new2old[first + i];
+    dst[i] = (o == 0xFFFFFFFFu) ? 0.0 : x_orig[o] / nrm;
+  }
+}
+// same without scaling
+__global__ void k_permute_in_raw(const double* __restrict__ x_orig, const uint32_t* __restrict__ new2old, uint64_t first, uint64_t count,
+                                 double* __restrict__ dst) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t o = new2old[first + i];
+    dst[i] = (o == 0xFFFFFFFFu) ? 0.0 : x_orig[o];
+  }
+}
+__global__ void k_fill(double* __restrict__ p, uint64_t n, double v) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// y_orig[new2old[i]] = y_new[i]
+__global__ void k_permute_out(const double* __restrict__ y_new, const uint32_t* __restrict__ new2old, uint64_t count,
+                              double* __restrict__ y_orig) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t o = new2old[i];
+    if (o != 0xFFFFFFFFu) y_orig[o] = y_new[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------- tall-skinny GEMV-T (reorth dots)
+// h[t] = sum_i V[t][i] w[i], t < nvec. Vectors are processed in register tiles of TILE so w is re-read nvec/TILE times
+// (+1/TILE traffic) while TILE independent 16-byte loads per thread are in flight.
+constexpr int kDotTile = 8;
+__global__ void __launch_bounds__(kBlock) k_multidot(const double* __restrict__ V, uint64_t ldv, uint32_t nvec, const double* __restrict__ w,
+                                                     uint64_t n, double* partials /* [nvec][grid] */, unsigned int* ticket, double* h_out) {
+  __shared__ double sm[kWarps];
+  __shared__ bool s_last;
+  const uint64_t n2 = n >> 1;
+  const double2* w2 = reinterpret_cast<const double2*>(w);
+  for (uint32_t t0 = 0; t0 < nvec; t0 += kDotTile) {
+    double acc[kDotTile];
+#pragma unroll
+    for (int u = 0; u < kDotTile; u++) acc[u] = 0.0;
+    const uint32_t nt = min((uint32_t)kDotTile, nvec - t0);
+    const double2* v2 = reinterpret_cast<const double2*>(V + (uint64_t)t0 * ldv);
+    const uint64_t ld2 = ldv >> 1;
+    if (nt == kDotTile) {
+      for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
+        const double2 wv = w2[i];
+        double2 vv[kDotTile];
+#pragma unroll
+        for (int u = 0; u < kDotTile; u++) vv[u] = __ldcs(v2 + (uint64_t)u * ld2 + i);
+#pragma unroll
+        for (int u = 0; u < kDotTile; u++) { acc[u] += vv[u].x * wv.x; acc[u] += vv[u].y * wv.y; }
+      }
+    } else {
+      for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
+        const double2 wv = w2[i];
+#pragma unroll
+        for (int u = 0; u < kDotTile; u++)
+          if (u < (int)nt) { const double2 vv = __ldcs(v2 + (uint64_t)u * ld2 + i); acc[u] += vv.x * wv.x; acc[u] += vv.y * wv.y; }
+      }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+      for (int u = 0; u < kDotTile; u++)
+        if (u < (int)nt) acc[u] += V[(uint64_t)(t0 + u) * ldv + n - 1] * w[n - 1];
+    }
+#pragma unroll
+    for (int u = 0; u < kDotTile; u++) {
+      if (u < (int)nt) {
+        double s = block_sum(acc[u], sm);
+        if (threadIdx.x == 0) partials[(uint64_t)(t0 + u) * gridDim.x + blockIdx.x] = s;
+      }
+    }
+  }
+  // last CTA: one warp per vector, lanes stride the CTA partials in index order
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t t = wid; t < nvec; t += kWarps) {
+      double acc = 0.0;
+      for (unsigned int i = lane; i < gridDim.x; i += 32) acc += __ldcg(partials + (uint64_t)t * gridDim.x + i);
+      acc = warp_sum(acc);
+      if (lane == 0) h_out[t] = acc;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------- tall-skinny GEMV-N (reorth update, multOut)
+// out[i] = (base ? base[i] : 0) + sign * sum_t coef[t] V[t][i], accumulated in t order (the order of the reference's
+// row-major Trans dgemv, multiplyOut.cu:44). Optional partial of ||out||^2.
+__global__ void __launch_bounds__(kBlock) k_combine(const double* __restrict__ V, uint64_t ldv, uint32_t nvec, const double* __restrict__ coef,
+                                                    double sign, const double* base, double* out, uint64_t n, double* partials,
+                                                    unsigned int* ticket, double* norm2_out) {
+  extern __shared__ double s_coef[];
+  __shared__ double sm[kWarps];
+  __shared__ bool s_last;
+  for (uint32_t t = threadIdx.x; t < nvec; t += kBlock) s_coef[t] = sign * coef[t];
+  __syncthreads();
+  const uint64_t n2 = n >> 1, ld2 = ldv >> 1;
+  const double2* v2 = reinterpret_cast<const double2*>(V);
+  const double2* b2 = reinterpret_cast<const double2*>(base);
+  double2* o2 = reinterpret_cast<double2*>(out);
+  double nacc = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
+    double2 acc = base ? b2[i] : make_double2(0.0, 0.0);
+    uint32_t t = 0;
+    for (; t + 8 <= nvec; t += 8) {
+      double2 vv[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) vv[u] = __ldcs(v2 + (uint64_t)(t + u) * ld2 + i);
+#pragma unroll
+      for (int u = 0; u < 8; u++) { acc.x += s_coef[t + u] * vv[u].x; acc.y += s_coef[t + u] * vv[u].y; }
+    }
+    for (; t < nvec; t++) {
+      const double2 vv = __ldcs(v2 + (uint64_t)t * ld2 + i);
+      acc.x += s_coef[t] * vv.x;
+      acc.y += s_coef[t] * vv.y;
+    }
+    o2[i] = acc;
+    nacc += acc.x * acc.x;
+    nacc += acc.y * acc.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double acc = base ? base[n - 1] : 0.0;
+    for (uint32_t t = 0; t < nvec; t++) acc += s_coef[t] * V[(uint64_t)t * ldv + n - 1];
+    out[n - 1] = acc;
+    nacc += acc * acc;
+  }
+  if (norm2_out) {
+    nacc = block_sum(nacc, sm);
+    grid_sum_finish(nacc, partials, ticket, norm2_out, sm, &s_last);
+  }
+}
+
+// ------------------------------------------------------------------------------------ tridiagonal eigenproblem + coefficients
+// One CTA. Thread 0 runs the scalar implicit-shift QL recurrences and publishes each sweep's rotations; all threads apply
+// them to the eigenvector matrix, kept transposed (zt[i*k + q] = component q of vector i) so the update is coalesced.
+// Output in the layout LAPACKE_dstevd(LAPACK_ROW_MAJOR,'V') gives the reference (eigen.cu:20): eigenvalues ascending,
+// eigvecs[q*k + j] = component q of eigenvector j. Then f_j = exp(lambda_j) * x_norm * eigvecs[0*k + j] (multiplyOut.cu:30-33)
+// and coef = eigvecs * f (multiplyOut.cu:40).
+constexpr int kEigMax = 1024;
+__global__ void __launch_bounds__(kBlock) k_tridiag_expv(uint32_t k, const double* __restrict__ alpha, const double* __restrict__ beta,
+                                                         const double* __restrict__ xnorm2_p, double* __restrict__ eigvals,
+                                                         double* __restrict__ eigvecs, double* __restrict__ zt, double* __restrict__ coef,
+                                                         int* __restrict__ status) {
+  __shared__ double d[kEigMax], e[kEigMax], cs[kEigMax], sn[kEigMax];
+  __shared__ int perm[kEigMax];
+  __shared__ int s_m, s_sweep, s_cont, s_fail;
+  const int n = (int)k, tid = threadIdx.x;
+  for (int i = tid; i < n; i += kBlock) {
+    d[i] = alpha[i];
+    e[i] = (i + 1 < n) ? beta[i] : 0.0;
+  }
+  for (int i = tid; i < n * n; i += kBlock) zt[i] = ((i / n) == (i % n)) ? 1.0 : 0.0;
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  const double eps = 2.220446049250313e-16;
+  double f = 0.0, tst1 = 0.0;   // live in thread 0 only
+  for (int l = 0; l < n; l++) {
+    int iter = 0;
+    if (tid == 0) {
+      tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
+      int m = l;
+      while (m < n - 1 && fabs(e[m]) > eps * tst1) m++;   // e[n-1] == 0; written so a NaN input cannot run past the end
+      s_m = m;
+    }
+    __syncthreads();
+    const int m = s_m;
+    if (m > l) {
+      for (;;) {
+        if (tid == 0) {
+          s_sweep = 1;
+          if (++iter > 60) { s_fail = l + 1; s_sweep = 0; s_cont = 0; }
+          else {
+            double g = d[l];
+            double p = (d[l + 1] - g) / (2.0 * e[l]);
+            double r = hypot(p, 1.0);
+            if (p < 0) r = -r;
+            d[l] = e[l] / (p + r);
+            d[l + 1] = e[l] * (p + r);
+            const double dl1 = d[l + 1];
+            double h = g - d[l];
+            for (int i = l + 2; i < n; i++) d[i] -= h;
+            f += h;
+            p = d[m];
+            double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0;
+            const double el1 = e[l + 1];
+            for (int i = m - 1; i >= l; i--) {
+              c3 = c2; c2 = c; s2 = s;
+              g = c * e[i];
+              h = c * p;
+              r = hypot(p, e[i]);
+              e[i + 1] = s * r;
+              s = e[i] / r;
+              c = p / r;
+              p = c * d[i] - s * g;
+              d[i + 1] = h + s * (c * g + s * d[i]);
+              cs[i] = c; sn[i] = s;
+            }
+            p = -s * s2 * c3 * el1 * e[l] / dl1;
+            e[l] = s * p;
+            d[l] = c * p;
+            s_cont = fabs(e[l]) > eps * tst1;
+          }
+        }
+        __syncthreads();
+        if (s_sweep) {
+          for (int q = tid; q < n; q += kBlock) {
+            for (int i = m - 1; i >= l; i--) {
+              const double c = cs[i], s = sn[i];
+              const double h = zt[(i + 1) * n + q], z = zt[i * n + q];
+              zt[(i + 1) * n + q] = s * z + c * h;
+              zt[i * n + q] = c * z - s * h;
+            }
+          }
+        }
+        const int cont = s_cont;
+        __syncthreads();
+        if (!cont) break;
+      }
+    }
+    if (tid == 0) { d[l] += f; e[l] = 0.0; }
+    __syncthreads();
+    if (s_fail) break;
+  }
+  // ascending order (rank by counting; ties by index)
+  for (int i = tid; i < n; i += kBlock) {
+    int r = 0;
+    const double di = d[i];
+    for (int j = 0; j < n; j++) r += (d[j] < di) || (d[j] == di && j < i);
+    perm[r] = i;
+  }
+  __syncthreads();
+  for (int j = tid; j < n; j += kBlock) eigvals[j] = d[perm[j]];
+  for (int i = tid; i < n * n; i += kBlock) {
+    const int q = i / n, j = i % n;
+    eigvecs[i] = zt[perm[j] * n + q];
+  }
+  __syncthreads();
+  const double xn = sqrt(*xnorm2_p);
+  for (int j = tid; j < n; j += kBlock) cs[j] = exp(d[perm[j]]) * xn * eigvecs[j];   // f_j ; row 0 of eigvecs
+  __syncthreads();
+  bool bad = false;
+  for (int i = tid; i < n; i += kBlock) {
+    double s = 0.0;
+    for (int j = 0; j < n; j++) s += eigvecs[(size_t)i * n + j] * cs[j];
+    coef[i] = s;
+    bad |= !isfinite(s);
+  }
+  if (tid == 0) *status = s_fail;
+  __syncthreads();
+  if (bad) atomicOr(status, 0x40000000);
+}
+
+inline unsigned stream_grid(const lz_ctx* c, uint64_t work_items /* per-thread items */) {
+  uint64_t want = (work_items + kBlock - 1) / kBlock;
+  uint64_t cap = (uint64_t)c->sm_count * 8;
+  if (want < 1) want = 1;
+  return (unsigned)(want < cap ? want : cap);
+}
+
+}  // namespace
+
+#define LZ_LAUNCH_CHECK()                                                                         \
+  do {                                                                                            \
+    cudaError_t e_ = cudaGetLastError();                                                          \
+    if (e_ != cudaSuccess) return lz_fail(LZ_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    c->launches++;                                                                                \
+  } while (0)
+
+static int ensure_partials(lz_ctx* c, uint64_t count) {
+  if (count <= c->partials_cap) return LZ_OK;
+  // only grows between runs; in-flight kernels are ordered on the same stream, and cudaFree synchronises
+  cudaFree(c->partials);
+  c->partials = nullptr; c->partials_cap = 0;
+  LZ_CUDA(cudaMalloc((void**)&c->partials, count * sizeof(double)));
+  c->partials_cap = (uint32_t)count;
+  return LZ_OK;
+}
+
+int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out) {
+  const lz_spmv_plan& plan = c->plan;
+  if (plan.nblocks == 0) return lz_fail(LZ_ERR_ARG, "empty SpMV plan");
+  LZ_TRY(ensure_partials(c, plan.nblocks));
+  k_spmv_dot<<<plan.nblocks, kBlock, 0, c->stream>>>(plan, c->row_ptr, c->col, x_gather, q_local, w_out, c->partials, c->ticket + 0, alpha_out);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev, const double* alpha, const double* beta_prev,
+                     double* norm2_out) {
+  unsigned g = stream_grid(c, c->n_loc / 2 + 1);
+  LZ_TRY(ensure_partials(c, g));
+  k_update_norm<<<g, kBlock, 0, c->stream>>>(w, qj, qprev, alpha, beta_prev, c->n_loc, c->partials, c->ticket + 1, norm2_out);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* q_next_copy, double* beta_out) {
+  unsigned g = stream_grid(c, c->n_loc / 2 + 1);
+  k_scale<<<g, kBlock, 0, c->stream>>>(w, norm2, c->n_loc, q_next, q_next_copy, beta_out);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_norm2(lz_ctx* c, const double* v, uint64_t len, double* out) {
+  unsigned g = stream_grid(c, len);
+  LZ_TRY(ensure_partials(c, g));
+  k_norm2<<<g, kBlock, 0, c->stream>>>(v, len, c->partials, c->ticket + 2, out);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_multidot(lz_ctx* c, const double* V, uint32_t nvec, const double* w, double* h_out) {
+  unsigned g = (unsigned)c->sm_count * 4;
+  uint64_t want = (c->n_loc / 2 + kBlock) / kBlock;
+  if (want < g) g = (unsigned)(want ? want : 1);
+  LZ_TRY(ensure_partials(c, (uint64_t)g * nvec));
+  k_multidot<<<g, kBlock, 0, c->stream>>>(V, c->ldv, nvec, w, c->n_loc, c->partials, c->ticket + 3, h_out);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_combine(lz_ctx* c, const double* V, uint32_t nvec, const double* coef, double coef_sign, const double* base, double* out,
+                 double* norm2_out) {
+  unsigned g = stream_grid(c, c->n_loc / 2 + 1);
+  LZ_TRY(ensure_partials(c, g));
+  k_combine<<<g, kBlock, nvec * sizeof(double), c->stream>>>(V, c->ldv, nvec, coef, coef_sign, base, out, c->n_loc, c->partials,
+                                                             c->ticket + 4, norm2_out);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_tridiag_expv(lz_ctx* c, uint32_t k) {
+  if (k > (uint32_t)kEigMax) return lz_fail(LZ_ERR_ARG, "krylov dimension %u exceeds the on-device eigensolver limit %d", k, kEigMax);
+  k_tridiag_expv<<<1, kBlock, 0, c->stream>>>(k, c->alpha, c->beta, c->scal + 2, c->eigvals, c->eigvecs, c->eigwork, c->coef, c->status);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_permute_in(lz_ctx* c, const double* x_orig, const double* norm2, uint64_t first, uint64_t count, double* dst) {
+  unsigned g = stream_grid(c, count);
+  if (norm2) k_permute_in<<<g, kBlock, 0, c->stream>>>(x_orig, c->new2old, first, count, norm2, dst);
+  else k_permute_in_raw<<<g, kBlock, 0, c->stream>>>(x_orig, c->new2old, first, count, dst);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_permute_out(lz_ctx* c, const double* y_new_full, double* y_orig) {
+  uint64_t count = c->n_loc * (uint64_t)c->world;
+  unsigned g = stream_grid(c, count);
+  k_permute_out<<<g, kBlock, 0, c->stream>>>(y_new_full, c->new2old, count, y_orig);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_fill(lz_ctx* c, double* p, uint64_t n, double value) {
+  k_fill<<<stream_grid(c, n), kBlock, 0, c->stream>>>(p, n, value);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}

@@ -1,0 +1,251 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the reference's golden output. All need a GPU.
+
+Tolerances (BASELINE.json north_star): e^A·x within 1e-9 relative 2-norm in fp64; top-100 ranking identical
+(argsort(-y), stable index tie-break on both sides). Integer-valued SpMV inputs must be bit-exact."""
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+CASES = ["c1_er_n10000_k20", "er_n2000_k20", "rmat_s12_k30", "rmat_s14_k50", "band_n4096_k40", "er_n257_k10_ragged"]
+
+
+def rel2(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.fixture(scope="module")
+def ctx(lz):
+    c = lz.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_expv_matches_reference_golden(lz, orc, golden, ctx, name):
+    g = golden(name)
+    ro, ci, k, n = g["row_offset"], g["col_idx"], int(g["k"]), int(g["n"])
+    ctx.csr_upload(ro, ci)
+    y = ctx.expv_host(None, k)                      # x = ones, as every reference driver (main.cu:79)
+    assert rel2(y, g["ans"]) < TOL
+    assert orc.top_gap(g["ans"]) > 1e-6             # the ranking claim is meaningful
+    assert np.array_equal(orc.top_k(y), orc.top_k(g["ans"]))
+    alpha, beta = ctx.get_tridiag()
+    np.testing.assert_allclose(alpha, g["alpha"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(beta[: max(k // 2, 1)], g["beta"][: max(k // 2, 1)], rtol=1e-7)
+    # random start vector from host memory
+    y2 = ctx.expv_host(g["x_random"], k)
+    assert rel2(y2, g["ans_random"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["er_n2000_k20", "rmat_s12_k30", "rmat_s14_k50"])
+def test_full_reorth_within_tolerance_of_plain_reference(lz, orc, golden, ctx, name):
+    g = golden(name)
+    ro, ci, k, n = g["row_offset"], g["col_idx"], int(g["k"]), int(g["n"])
+    ctx.csr_upload(ro, ci)
+    y = ctx.expv_host(None, k, lz.REORTH_FULL)
+    assert rel2(y, g["ans"]) < TOL
+    assert np.array_equal(orc.top_k(y), orc.top_k(g["ans"]))
+    ans_o, alpha_o, _ = orc.expv(ro, ci, k, np.ones(n), reorth=orc.FULL)     # our CGS2 spec on the CPU
+    assert rel2(y, ans_o) < TOL
+    # basis is orthonormal to working precision
+    Q = np.stack([ctx.get_basis(j) for j in range(k)])
+    assert np.abs(Q @ Q.T - np.eye(k)).max() < 1e-12
+
+
+@pytest.mark.parametrize("variant", ["auto", "warp"])
+@pytest.mark.parametrize("spec_name", ["er", "rmat", "band", "tiny"])
+def test_spmv_bit_exact_on_integer_data(lz, orc, ctx, spec_name, variant):
+    spec = {"er": lz.GraphSpec.er(30011, 150000, 5), "rmat": lz.GraphSpec.rmat(15, 8, 3),
+            "band": lz.GraphSpec.band(20000, 9), "tiny": lz.GraphSpec.er(33, 40, 1)}[spec_name]
+    n, ro, ci = lz.generate_host(spec)
+    ctx.set_spmv_variant(lz.SPMV_WARP if variant == "warp" else lz.SPMV_AUTO)
+    try:
+        ctx.csr_upload(ro, ci)
+        rng = np.random.default_rng(7)
+        x = rng.integers(-(1 << 20), 1 << 20, n).astype(np.float64)     # sums are exact in fp64 in any order
+        assert np.array_equal(ctx.spmv_host(x), orc.spmv(ro, ci, x))
+        assert np.array_equal(ctx.spmv_host(np.ones(n)), np.diff(ro).astype(np.float64))
+        xr = rng.random(n)
+        y, yo = ctx.spmv_host(xr), orc.spmv(ro, ci, xr)
+        assert np.abs(y - yo).max() <= 64 * np.finfo(float).eps * max(1.0, np.abs(yo).max())
+    finally:
+        ctx.set_spmv_variant(lz.SPMV_AUTO)
+
+
+@pytest.mark.parametrize("spec_name", ["er", "rmat", "band"])
+def test_device_generator_matches_host_generator(lz, ctx, spec_name):
+    spec = {"er": lz.GraphSpec.er(50000, 300000, 11), "rmat": lz.GraphSpec.rmat(16, 8, 1),
+            "band": lz.GraphSpec.band(70001, 5)}[spec_name]
+    n, ro, ci = lz.generate_host(spec)
+    ctx.graph_generate(spec)
+    ro_d, ci_d = ctx.csr_download()
+    assert np.array_equal(ro, ro_d) and np.array_equal(ci, ci_d)
+    gi = ctx.graph_info()
+    deg = np.diff(ro)
+    assert (gi.n, gi.nnz, gi.max_degree, gi.empty_rows) == (n, len(ci), deg.max(), int((deg == 0).sum()))
+
+
+def test_first_basis_vector_and_alpha0(lz, orc, golden, ctx):
+    g = golden("rmat_s12_k30")
+    ro, ci, n = g["row_offset"], g["col_idx"], int(g["n"])
+    ctx.csr_upload(ro, ci)
+    ctx.set_start_vector(g["x_random"])
+    ctx.lanczos_run(3)
+    q0 = ctx.get_basis(0)
+    x = g["x_random"]
+    np.testing.assert_allclose(q0, x / np.linalg.norm(x), rtol=1e-15)
+    a_o, b_o, Q_o = orc.lanczos(ro, ci, 3, x)
+    alpha, beta = ctx.get_tridiag()
+    np.testing.assert_allclose(alpha, a_o, rtol=1e-12)
+    np.testing.assert_allclose(beta, b_o, rtol=1e-12)
+    for j in range(3):
+        assert rel2(ctx.get_basis(j), Q_o[:, j]) < 1e-11
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 64, 200])
+def test_device_tridiag_solver_vs_oracle(lz, orc, ctx, k):
+    """Runs Lanczos for k steps and compares the on-device eigen-solve + coefficient vector with the oracle's
+    restatement of dstevd on the same (alpha, beta) — sign-free quantities only."""
+    n, ro, ci = lz.generate_host(lz.GraphSpec.er(3000, 9000, 21))
+    ctx.csr_upload(ro, ci)
+    ctx.set_start_vector(None)
+    ctx.lanczos_run(k, lz.REORTH_FULL if k > 30 else lz.REORTH_NONE)
+    alpha, beta = ctx.get_tridiag()
+    ctx.tridiag_expv()
+    w, Z, c = ctx.get_eigen()
+    w_o, Z_o = orc.tridiag_eig(alpha, beta)
+    np.testing.assert_allclose(w, w_o, rtol=0, atol=1e-12 * max(1.0, np.abs(w_o).max()))
+    T = np.diag(alpha) + (np.diag(beta, 1) + np.diag(beta, -1) if k > 1 else 0)
+    assert np.abs(T @ Z - Z * w).max() < 1e-11 * max(1.0, np.abs(w).max())
+    assert np.abs(Z.T @ Z - np.eye(k)).max() < 1e-12
+    c_o = np.sqrt(n) * (Z_o @ (np.exp(w_o) * Z_o[0]))
+    assert rel2(c, c_o) < 1e-11
+
+
+def test_multout_is_idempotent_and_matches_manual_combination(lz, orc, golden, ctx):
+    """The reference's multOut mutates E in place and cannot be called twice; ours can."""
+    g = golden("er_n2000_k20")
+    ro, ci, k, n = g["row_offset"], g["col_idx"], int(g["k"]), int(g["n"])
+    ctx.csr_upload(ro, ci)
+    ctx.set_start_vector(None)
+    ctx.lanczos_run(k)
+    ctx.tridiag_expv()
+    ctx.multout()
+    y1 = ctx.get_ans()
+    ctx.multout()
+    y2 = ctx.get_ans()
+    assert np.array_equal(y1, y2)
+    _, _, c = ctx.get_eigen()
+    Q = np.stack([ctx.get_basis(j) for j in range(k)])
+    assert rel2(y1, c @ Q) < 1e-14
+    assert rel2(y1, g["ans"]) < TOL
+
+
+def test_krylov_dimension_edge_cases(lz, orc, ctx):
+    n, ro, ci = lz.generate_host(lz.GraphSpec.er(500, 2000, 2))
+    ctx.csr_upload(ro, ci)
+    x = np.ones(n)
+    for k in (1, 2, 3):
+        y = ctx.expv_host(x, k)
+        yo, _, _ = orc.expv(ro, ci, k, x)
+        assert rel2(y, yo) < 1e-12, k
+    with pytest.raises(lz.LzError):
+        ctx.lanczos_run(0)
+    with pytest.raises(lz.LzError):
+        ctx.lanczos_run(5, 7)
+
+
+def test_call_order_errors(lz):
+    with lz.Context(0) as c:
+        with pytest.raises(lz.LzError):
+            c.set_start_vector(None)          # no graph
+        n, ro, ci = lz.generate_host(lz.GraphSpec.er(100, 300, 2))
+        c.csr_upload(ro, ci)
+        with pytest.raises(lz.LzError):
+            c.lanczos_run(5)                  # no start vector
+        c.set_start_vector(None)
+        with pytest.raises(lz.LzError):
+            c.tridiag_expv()                  # no decomposition
+        c.lanczos_run(5)
+        with pytest.raises(lz.LzError):
+            c.multout()                       # no coefficients
+
+
+def test_breakdown_is_reported_not_silent(lz, ctx):
+    """Regular graph + constant x: A.1 = d.1 so beta_0 = 0 — the reference divides by zero and returns NaN
+    (SURVEY 7.3-2). We must surface it as an error, not hand back NaNs as if they were a result."""
+    n = 64
+    ro = np.arange(0, 2 * n + 1, 2, dtype=np.uint32)
+    ci = np.empty(2 * n, np.uint32)
+    for i in range(n):
+        ci[2 * i: 2 * i + 2] = sorted(((i - 1) % n, (i + 1) % n))
+    ctx.csr_upload(ro, ci)
+    with pytest.raises(lz.LzError) as e:
+        ctx.expv_host(None, 5)
+    assert e.value.code == -6
+    y = ctx.expv_host(None, 1)                # k = 1 never divides: e^2 * 1
+    np.testing.assert_allclose(y, np.exp(2.0), rtol=1e-14)
+
+
+@pytest.mark.parametrize("scale,k", [(20, 30)])
+def test_c2_size_against_oracle(lz, orc, ctx, scale, k):
+    """BASELINE.json configs[1]: R-MAT 2^20, ~16 nnz/row, k=30, fp64 e^A·x + top-100 ranking, vs the CPU oracle
+    (and vs the compiled reference itself when oracle/_ref is present)."""
+    spec = lz.GraphSpec.rmat(scale, 8, 1)
+    ctx.graph_generate(spec)
+    ro, ci = ctx.csr_download()
+    n = len(ro) - 1
+    y = ctx.expv_host(None, k)
+    if orc.have_ref():
+        ref = orc.run_ref_final(ro, ci, k)["ans"]
+    else:
+        ref, _, _ = orc.expv(ro, ci, k, np.ones(n))
+    assert np.isfinite(ref).all()
+    assert rel2(y, ref) < TOL
+    assert orc.top_gap(ref) > 1e-7
+    assert np.array_equal(orc.top_k(y), orc.top_k(ref))
+    yr = ctx.expv_host(None, k, lz.REORTH_FULL)
+    assert rel2(yr, ref) < TOL and np.array_equal(orc.top_k(yr), orc.top_k(ref))
+
+
+def test_full_size_properties_c3(lz, orc, ctx):
+    """BASELINE.json configs[2] size (R-MAT 2^24, k=50): too big for the CPU oracle inside a test, so check
+    size-independent properties: SpMV of ones = degree vector (exact), linearity of SpMV on integer data (exact),
+    Lanczos basis orthonormality under full reorth, T = Q^T A Q consistency (alpha_j = q_j.A.q_j), k-convergence
+    (k=40 vs k=50 agree), and determinism (two runs bit-identical)."""
+    spec = lz.GraphSpec.rmat(24, 8, 1)
+    ctx.graph_generate(spec)
+    gi = ctx.graph_info()
+    n = gi.n
+    assert n == 1 << 24 and 15.5 < gi.nnz / n < 16.0
+    ro, ci = ctx.csr_download()
+    deg = np.diff(ro).astype(np.float64)
+    assert np.array_equal(ctx.spmv_host(np.ones(n)), deg)
+    rng = np.random.default_rng(3)
+    a = rng.integers(-1000, 1000, n).astype(np.float64)
+    b = rng.integers(-1000, 1000, n).astype(np.float64)
+    ya, yb, yab = ctx.spmv_host(a), ctx.spmv_host(b), ctx.spmv_host(2 * a - 3 * b)
+    assert np.array_equal(yab, 2 * ya - 3 * yb)
+    # spot-check rows against a direct gather-sum
+    rows = rng.integers(0, n, 2000)
+    for r in rows[:200]:
+        assert ya[r] == a[ci[ro[r]:ro[r + 1]]].sum()
+    y50 = ctx.expv_host(None, 50)
+    alpha, beta = ctx.get_tridiag()
+    assert np.isfinite(y50).all() and np.all(beta > 0)
+    q0, q1 = ctx.get_basis(0), ctx.get_basis(1)
+    assert abs(q0 @ q1) < 1e-12 and abs(q1 @ q1 - 1) < 1e-12
+    assert abs(q1 @ ctx.spmv_host(q1) - alpha[1]) < 1e-9 * abs(alpha[1])
+    y50b = ctx.expv_host(None, 50)
+    assert np.array_equal(y50, y50b)                               # deterministic reductions
+    y40 = ctx.expv_host(None, 40)
+    assert rel2(y40, y50) < 1e-9
+    assert np.array_equal(orc.top_k(y40), orc.top_k(y50))
+    y50r = ctx.expv_host(None, 50, lz.REORTH_FULL)
+    assert rel2(y50r, y50) < TOL and np.array_equal(orc.top_k(y50r), orc.top_k(y50))
+    qa, qb = ctx.get_basis(49), ctx.get_basis(3)
+    assert abs(qa @ qb) < 1e-12 and abs(qa @ qa - 1) < 1e-12

@@ -1,0 +1,146 @@
+"""Pins the CPU oracle (oracle/lanczos_oracle.c) against the reference's own output.
+
+Golden vectors in tests/golden/*.npz were produced by the UNMODIFIED reference compiled into oracle/_ref (see
+tests/golden/make_golden.py). Where oracle/_ref exists (build container, and the GPU box via gpurun) the reference is also
+re-run live on a fresh seed. No GPU needed."""
+import json
+
+import numpy as np
+import pytest
+
+CASES = ["c1_er_n10000_k20", "er_n2000_k20", "rmat_s12_k30", "rmat_s14_k50", "band_n4096_k40", "er_n257_k10_ragged"]
+
+
+def rel2(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_generator_reproduces_golden_graph(lz, golden, name):
+    g = golden(name)
+    s = json.loads(str(g["spec"]))
+    spec = lz.GraphSpec(**s)
+    n, ro, ci = lz.generate_host(spec)
+    assert n == int(g["n"])
+    assert np.array_equal(ro, g["row_offset"]) and np.array_equal(ci, g["col_idx"])
+    # simple undirected graph: symmetric, no self loops, sorted unique columns, last vertex not isolated
+    rows = np.repeat(np.arange(n, dtype=np.uint32), np.diff(ro))
+    assert not np.any(rows == ci)
+    fwd = set(zip(rows.tolist(), ci.tolist()))
+    assert len(fwd) == len(ci) and all((c, r) in fwd for r, c in list(fwd)[:2000])
+    assert ro[n] > ro[n - 1]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(orc, golden, name):
+    g = golden(name)
+    ro, ci, k, n = g["row_offset"], g["col_idx"], int(g["k"]), int(g["n"])
+    ans, alpha, beta = orc.expv(ro, ci, k, np.ones(n))
+    # the recurrence is restated operation by operation: alpha/beta must match the reference to the last bits
+    np.testing.assert_allclose(alpha, g["alpha"], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(beta, g["beta"], rtol=1e-13, atol=0)
+    assert rel2(ans, g["ans"]) < 1e-12
+    assert np.array_equal(orc.top_k(ans), orc.top_k(g["ans"]))
+    # the reference's own serial/ tree agrees with its parallel-final host path
+    assert rel2(g["ans_serial"], g["ans"]) < 1e-14
+    # random start vector
+    ans_r, alpha_r, _ = orc.expv(ro, ci, k, g["x_random"])
+    np.testing.assert_allclose(alpha_r, g["alpha_random"], rtol=1e-13, atol=0)
+    assert rel2(ans_r, g["ans_random"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["er_n2000_k20", "rmat_s12_k30", "band_n4096_k40"])
+def test_oracle_arnoldi_variant_matches_serial_reference(orc, golden, name):
+    g = golden(name)
+    ro, ci, k, n = g["row_offset"], g["col_idx"], int(g["k"]), int(g["n"])
+    ans, alpha, _ = orc.expv(ro, ci, k, np.ones(n), reorth=orc.ARNOLDI)
+    np.testing.assert_allclose(alpha, g["alpha_arnoldi"], rtol=1e-12, atol=1e-12)
+    assert rel2(ans, g["ans_arnoldi"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["er_n2000_k20", "rmat_s12_k30"])
+def test_full_reorth_spec_agrees_with_plain_reference(orc, golden, name):
+    """LZ_REORTH_FULL's specification (CGS2 every step) stays within the 1e-9 bar of the reference's plain answer."""
+    g = golden(name)
+    ro, ci, k, n = g["row_offset"], g["col_idx"], int(g["k"]), int(g["n"])
+    ans, _, _ = orc.expv(ro, ci, k, np.ones(n), reorth=orc.FULL)
+    assert rel2(ans, g["ans"]) < 1e-9
+    assert np.array_equal(orc.top_k(ans), orc.top_k(g["ans"]))
+    # and the basis really is orthonormal
+    _, _, Q = orc.lanczos(ro, ci, k, np.ones(n), reorth=orc.FULL)
+    assert np.abs(Q.T @ Q - np.eye(k)).max() < 1e-13
+
+
+def test_spmv_restatement(orc, golden):
+    g = golden("rmat_s12_k30")
+    ro, ci, n = g["row_offset"], g["col_idx"], int(g["n"])
+    assert np.array_equal(orc.spmv(ro, ci, np.ones(n)), np.diff(ro).astype(np.float64))   # A.1 = degrees, exact
+    rng = np.random.default_rng(0)
+    x = rng.integers(-1000, 1000, n).astype(np.float64)                                    # integer data: exact sums
+    import scipy.sparse as sp
+    A = sp.csr_matrix((np.ones(len(ci)), ci, ro), shape=(n, n))
+    assert np.array_equal(orc.spmv(ro, ci, x), A @ x)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 17, 50, 100])
+def test_tridiag_restatement_vs_lapack(orc, k):
+    """lzo_tridiag_eig states dstevd's contract; LAPACK (via SciPy) is the third-party arithmetic the reference calls."""
+    from scipy.linalg import eigh_tridiagonal
+    rng = np.random.default_rng(k)
+    a, b = rng.normal(size=k) * 5, np.abs(rng.normal(size=max(k - 1, 0))) + 0.1
+    w, Z = orc.tridiag_eig(a, b)
+    if k == 1:
+        assert w[0] == a[0] and abs(Z[0, 0]) == 1.0
+        return
+    w_ref, Z_ref = eigh_tridiagonal(a, b)
+    np.testing.assert_allclose(w, w_ref, rtol=0, atol=1e-13 * max(1.0, np.abs(w_ref).max()))
+    T = np.diag(a) + np.diag(b, 1) + np.diag(b, -1)
+    assert np.abs(T @ Z - Z * w).max() < 1e-12 * max(1.0, np.abs(w).max())
+    assert np.abs(Z.T @ Z - np.eye(k)).max() < 1e-13
+    # sign-free functional used by multOut: Z (e^w . Z[0,:])
+    c, c_ref = Z @ (np.exp(w) * Z[0]), Z_ref @ (np.exp(w_ref) * Z_ref[0])
+    assert rel2(c, c_ref) < 1e-12
+
+
+def test_multout_layouts_agree(orc, golden):
+    g = golden("er_n257_k10_ragged")
+    ro, ci, k, n = g["row_offset"], g["col_idx"], int(g["k"]), int(g["n"])
+    a, b, Q = orc.lanczos(ro, ci, k, np.ones(n))
+    w, Z = orc.tridiag_eig(a, b)
+    y0, c0 = orc.multout(w, Z, Q, np.sqrt(n), qtrans=False)
+    y1, c1 = orc.multout(w, Z, np.ascontiguousarray(Q.T), np.sqrt(n), qtrans=True)
+    assert np.array_equal(c0, c1) and rel2(y1, y0) < 1e-15
+    assert rel2(y0, g["ans"]) < 1e-12
+
+
+def test_oracle_vs_scipy_expm_multiply(orc, golden):
+    """Independent check of the whole method (5.7e-13 on C1)."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.linalg import expm_multiply
+    g = golden("c1_er_n10000_k20")
+    ro, ci, n = g["row_offset"], g["col_idx"], int(g["n"])
+    A = csr_matrix((np.ones(len(ci)), ci, ro), shape=(n, n))
+    y = expm_multiply(A, np.ones(n))
+    assert rel2(g["ans"], y) < 1e-11
+    assert np.array_equal(orc.top_k(g["ans"]), orc.top_k(y))
+
+
+def test_check_ans_and_ranking_helpers(orc):
+    a = np.array([1.0, 5.0, 5.0, 2.0, -3.0])
+    b = np.array([1.0, 5.0, 4.0, 2.0, -3.0])
+    mx, mi, nd, rel = orc.check_ans(a, b)
+    assert (mx, mi) == (1.0, 2) and nd == 1.0 and rel == pytest.approx(1.0 / np.linalg.norm(b))
+    assert orc.top_k(a, 3).tolist() == [1, 2, 3]          # tie -> lower index first
+
+
+def test_live_reference_on_fresh_seed(lz, orc):
+    """Re-runs the compiled reference (oracle/_ref) when present: fresh seed, CSR injection."""
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    n, ro, ci = lz.generate_host(lz.GraphSpec.rmat(13, 8, 99))
+    r = orc.run_ref_final(ro, ci, 30)
+    ans, alpha, beta = orc.expv(ro, ci, 30, np.ones(n))
+    np.testing.assert_allclose(alpha, r["alpha"], rtol=1e-13)
+    np.testing.assert_allclose(beta, r["beta"], rtol=1e-13)
+    assert rel2(ans, r["ans"]) < 1e-12
+    assert np.array_equal(orc.top_k(ans), orc.top_k(r["ans"]))
