@@ -436,10 +436,18 @@ __global__ void __launch_bounds__(kBlock) k_tridiag_expv(uint32_t k, const doubl
     if (s_fail) break;
   }
   // ascending order (rank by counting; ties by index)
+  // NaNs (Lanczos breakdown upstream) are ordered last so perm stays a permutation and nothing indexes out of range
   for (int i = tid; i < n; i += kBlock) {
     int r = 0;
     const double di = d[i];
-    for (int j = 0; j < n; j++) r += (d[j] < di) || (d[j] == di && j < i);
+    const bool ni = isnan(di);
+    for (int j = 0; j < n; j++) {
+      const double dj = d[j];
+      const bool nj = isnan(dj);
+      const bool less = ni ? (!nj) : (!nj && dj < di);
+      const bool same = ni ? nj : (!nj && dj == di);
+      r += less || (same && j < i);
+    }
     perm[r] = i;
   }
   __syncthreads();
