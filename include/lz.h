@@ -132,10 +132,11 @@ int lz_expv_host(lz_ctx* ctx, const double* x_host, uint32_t k, int reorth, doub
 int lz_spmv_host(lz_ctx* ctx, const double* x_host, double* y_host);
 /* Basis vector q_j (original order, full length) to the host. */
 int lz_get_basis(lz_ctx* ctx, uint32_t j, double* q_host);
-/* Selects the SpMV kernel variant: 0 = auto (by row-length distribution), else LZ_SPMV_* below. */
-#define LZ_SPMV_AUTO 0
-#define LZ_SPMV_VECTOR 1   /* sub-warp (2..32 lanes) per row, lanes chosen per degree bin */
-#define LZ_SPMV_WARP 2     /* one warp per row for every row                              */
+/* Selects the SpMV kernel variant. */
+#define LZ_SPMV_AUTO 0     /* default: by row length — warp per row for long rows, sliced (32 rows per warp, one lane
+                              per row, index stream transposed so it is read as whole lines) for the rest            */
+#define LZ_SPMV_VECTOR 1   /* CSR, sub-warp (1..32 lanes) per row, lanes chosen per degree bin                        */
+#define LZ_SPMV_WARP 2     /* CSR, one warp per row for every row                                                     */
 int lz_set_spmv_variant(lz_ctx* ctx, int variant);
 
 typedef struct lz_timings {

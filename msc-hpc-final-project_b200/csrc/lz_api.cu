@@ -9,6 +9,8 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <new>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 const lz_nccl_api* lz_nccl() {
@@ -149,6 +151,8 @@ static int create_common(int device, int rank, int world, const void* uid, lz_ct
   cudaDeviceProp prop;
   LZ_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("LZ_SPMV_VARIANT")) { int v = atoi(e); if (v >= 0 && v <= LZ_SPMV_WARP) c->spmv_variant = v; }     // tuning knob
+  if (const char* e = getenv("LZ_SPMV_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) c->spmv_ctas_per_sm = (uint32_t)v; }   // tuning knob
   LZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   LZ_CUDA(cudaEventCreate(&c->ev_a)); LZ_CUDA(cudaEventCreate(&c->ev_b));
   LZ_CUDA(cudaEventCreate(&c->ev_e0)); LZ_CUDA(cudaEventCreate(&c->ev_e1));
@@ -213,7 +217,6 @@ extern "C" int lz_sync(lz_ctx* c) {
 extern "C" int lz_set_spmv_variant(lz_ctx* c, int variant) {
   if (!c || variant < 0 || variant > LZ_SPMV_WARP) return lz_fail(LZ_ERR_ARG, "bad SpMV variant");
   c->spmv_variant = variant;
-  c->plan = (variant == LZ_SPMV_WARP) ? c->plan_warp : c->plan_auto;
   return LZ_OK;
 }
 

@@ -39,15 +39,20 @@ const lz_nccl_api* lz_nccl();   // nullptr (with lz_last_error set) when no libn
 // SpMV launch plan: local rows are sorted by length (non-increasing), so each bin is a contiguous row range that one
 // kernel variant (lanes-per-row = 1 << log2_lanes) serves.
 #define LZ_MAX_BINS 8
+#define LZ_MAX_COLBLK 32
+#define LZ_SELL_LONG 128          // rows longer than this are served warp-per-row
+#define LZ_SPMV_BLOCK 256         // threads per CTA of the SpMV kernel
+#define LZ_SPMV_ROWS_PER_GROUP 4  // rows handled concurrently by one lane group (memory-level parallelism)
 struct lz_spmv_bin {
   uint32_t row_begin, row_end;   // local rows [begin, end)
-  uint32_t log2_lanes;           // lanes cooperating on one row
-  uint32_t block_begin;          // first CTA of this bin in the fused launch
+  uint16_t log2_lanes;           // lanes cooperating on one row
+  uint16_t per_lane;             // entries each lane fetches per chunk (2 or 8); longer segments take further chunks
+  uint32_t item_begin;           // first work item of this bin; one item = (BLOCK >> log2_lanes) * ROWS_PER_GROUP rows
 };
 struct lz_spmv_plan {
   lz_spmv_bin bin[LZ_MAX_BINS];
   uint32_t nbins;
-  uint32_t nblocks;
+  uint32_t nitems;
 };
 
 struct lz_ctx {
@@ -72,8 +77,25 @@ struct lz_ctx {
   uint32_t* row_ptr = nullptr;     // device, local rows, [n_loc + 1]
   uint32_t* col = nullptr;         // device, [nnz_loc], NEW global column ids, ascending within a row
   uint32_t* new2old = nullptr;     // device, [n_loc * world]; 0xFFFFFFFF for padding slots
-  lz_spmv_plan plan_auto{}, plan_warp{}, plan{};
+  // Column blocking: the gathered vector is cut into ncolblk windows small enough to stay L2-resident; pass b of the
+  // SpMV handles the entries of every row whose column lies in window b. col[] is stored column-block-major, and
+  // seg[b] is the row pointer of block b ([n_loc + 1] entries, absolute positions into col[]).
+  uint32_t ncolblk = 1;
+  uint32_t* seg[LZ_MAX_COLBLK + 1] = {};
+  uint32_t* seg_store = nullptr;   // device, [ncolblk][n_loc + 1]
+  // Sliced layout used by the default SpMV (LZ_SPMV_AUTO): per column block, work items of 32 lanes.
+  //   item <  n_long : one long row (total length > LZ_SELL_LONG); its block slice is padded to a multiple of 32, lane l
+  //                    reads entries l, l+32, ... (warp per row, coalesced along the row)
+  //   item >= n_long : 32 consecutive rows, lane l owns row n_long + 32*(item - n_long) + l; entry j of the 32 rows is
+  //                    stored contiguously (sliced ELLPACK, slice height 32; rows are length-sorted so padding is small)
+  // sell_sp[b * n_items + item] = offset of the item in sell_col in units of 32 entries; padding = 0xFFFFFFFF.
+  uint32_t n_long = 0, n_items = 0;
+  uint32_t* sell_sp = nullptr;     // device, [ncolblk * n_items + 1]
+  uint32_t* sell_col = nullptr;    // device
+  uint64_t sell_entries = 0;       // padded entries stored (all blocks)
+  lz_spmv_plan plan_auto[LZ_MAX_COLBLK] = {}, plan_warp{};
   int spmv_variant = LZ_SPMV_AUTO;
+  uint32_t spmv_ctas_per_sm = 6;   // persistent SpMV grid = sm_count * this
 
   // ---- vectors ----------------------------------------------------------------------------------------------------
   uint64_t vec_n = 0, vec_nloc = 0; // graph size the vectors below were allocated for

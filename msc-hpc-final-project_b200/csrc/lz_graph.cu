@@ -17,6 +17,8 @@
 #include "lz_gen.h"
 
 #include <cub/cub.cuh>
+#include <stdlib.h>
+#include <vector>
 
 namespace {
 
@@ -83,10 +85,12 @@ __global__ void k_local_lengths(const uint32_t* __restrict__ sorted_old, const u
   len[l] = d;
 }
 
-// one warp per local row: keys[row_ptr[l] + j] = (l << 32) | old2new[ci[ro[old] + j]]
+// one warp per local row: keys[row_ptr[l] + j] = (colblock << (32 + rowbits)) | (l << 32) | newcol, newcol = old2new[ci[ro[old] + j]]
+// Sorting these keys lays col[] out column-block-major (each SpMV pass streams one contiguous piece), row-major inside
+// a block, ascending column inside a row slice.
 __global__ void k_local_keys(const uint32_t* __restrict__ sorted_old, const uint32_t* __restrict__ ro, const uint32_t* __restrict__ ci,
                              const uint32_t* __restrict__ old2new, const uint32_t* __restrict__ row_ptr, uint64_t n, uint32_t world,
-                             uint32_t rank, uint64_t n_loc, uint64_t* __restrict__ keys) {
+                             uint32_t rank, uint64_t n_loc, uint64_t width, int rowbits, uint64_t* __restrict__ keys) {
   uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint32_t lane = threadIdx.x & 31;
   if (warp >= n_loc) return;
@@ -94,7 +98,25 @@ __global__ void k_local_keys(const uint32_t* __restrict__ sorted_old, const uint
   if (s >= n) return;
   uint32_t old = sorted_old[s];
   uint32_t b = ro[old], e = ro[old + 1], dst = row_ptr[warp];
-  for (uint32_t j = b + lane; j < e; j += 32) keys[dst + (j - b)] = (warp << 32) | old2new[ci[j]];
+  for (uint32_t j = b + lane; j < e; j += 32) {
+    const uint32_t nc = old2new[ci[j]];
+    keys[dst + (j - b)] = ((uint64_t)(nc / width) << (32 + rowbits)) | (warp << 32) | nc;
+  }
+}
+
+// blk_rp[b * (n_loc + 1) + row] = first key position of (block b, row); row == n_loc gives the end of block b
+__global__ void k_block_row_ptr(const uint64_t* __restrict__ keys, uint64_t nnz, uint64_t n_loc, uint32_t nblk, int rowbits,
+                                uint32_t* __restrict__ blk_rp) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint64_t)nblk * (n_loc + 1)) return;
+  const uint64_t b = i / (n_loc + 1), row = i % (n_loc + 1);
+  const uint64_t target = (b << (32 + rowbits)) + (row << 32);   // row == n_loc may carry into the block field: intended
+  uint64_t lo = 0, hi = nnz;
+  while (lo < hi) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  blk_rp[i] = (uint32_t)lo;
 }
 
 // first local row whose length is <= thr[t]  (lengths are non-increasing)
@@ -109,6 +131,68 @@ __global__ void k_bin_bounds(const uint32_t* __restrict__ row_ptr, uint32_t n_lo
     if (len > thr[t]) lo = mid + 1; else hi = mid;
   }
   out[t] = lo;
+}
+
+// out[bin * nblk + b] = number of entries of column block b in the rows of bin `bin`  (grid = (nbins, nblk))
+__global__ void k_bin_block_nnz(const uint32_t* const* __restrict__ seg, const uint32_t* __restrict__ bin_rows /* [nbins+1] */,
+                                uint32_t nblk, unsigned long long* __restrict__ out) {
+  const uint32_t bin = blockIdx.x, b = blockIdx.y;
+  const uint32_t* lo = seg[b];
+  const uint32_t* hi = seg[b] + 1;
+  unsigned long long acc = 0;
+  for (uint32_t r = bin_rows[bin] + threadIdx.x; r < bin_rows[bin + 1]; r += blockDim.x) acc += hi[r] - lo[r];
+  __shared__ unsigned long long sm[256];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[bin * nblk + b] = sm[0];
+}
+
+// ---- sliced layout (see lz_ctx.h) -------------------------------------------------------------------------------
+// width (in chunks of 32 entries) of every (block, item). One warp per (block, item).
+__global__ void k_sell_widths(const uint32_t* const* __restrict__ seg, uint32_t nblk, uint32_t n_long, uint32_t n_items, uint32_t n_loc,
+                              uint32_t* __restrict__ widths /* [nblk * n_items + 1] */) {
+  const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (gw >= (uint64_t)nblk * n_items) return;
+  const uint32_t b = (uint32_t)(gw / n_items), item = (uint32_t)(gw % n_items);
+  const uint32_t* rp = seg[b];
+  uint32_t wdt;
+  if (item < n_long) {
+    wdt = (rp[item + 1] - rp[item] + 31) >> 5;
+  } else {
+    const uint32_t row = n_long + (item - n_long) * 32 + lane;
+    uint32_t len = row < n_loc ? rp[row + 1] - rp[row] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    wdt = len;
+  }
+  if (lane == 0) widths[gw] = wdt;
+}
+
+__global__ void k_sell_fill(const uint32_t* const* __restrict__ seg, const uint32_t* __restrict__ col, const uint32_t* __restrict__ sp,
+                            uint32_t nblk, uint32_t n_long, uint32_t n_items, uint32_t n_loc, uint32_t* __restrict__ out) {
+  const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (gw >= (uint64_t)nblk * n_items) return;
+  const uint32_t b = (uint32_t)(gw / n_items), item = (uint32_t)(gw % n_items);
+  const uint32_t* rp = seg[b];
+  const uint32_t c0 = sp[gw], nchunk = sp[gw + 1] - c0;
+  uint32_t* dst = out + (uint64_t)c0 * 32 + lane;
+  if (item < n_long) {
+    const uint32_t beg = rp[item], len = rp[item + 1] - beg;
+    for (uint32_t j = 0; j < nchunk; j++) {
+      const uint32_t idx = j * 32 + lane;
+      dst[(uint64_t)j * 32] = idx < len ? col[beg + idx] : 0xFFFFFFFFu;
+    }
+  } else {
+    const uint32_t row = n_long + (item - n_long) * 32 + lane;
+    const uint32_t beg = row < n_loc ? rp[row] : 0u, len = row < n_loc ? rp[row + 1] - beg : 0u;
+    for (uint32_t j = 0; j < nchunk; j++) dst[(uint64_t)j * 32] = j < len ? col[beg + j] : 0xFFFFFFFFu;
+  }
 }
 
 struct IsEmpty { __host__ __device__ uint64_t operator()(uint32_t k) const { return k == 0xFFFFFFFFu ? 1ull : 0ull; } };
@@ -127,27 +211,43 @@ int bits_for(uint64_t v) { int b = 0; while ((1ull << b) < v && b < 63) b++; ret
 }  // namespace
 
 void lz_free_graph(lz_ctx* c) {
-  cudaFree(c->orig_ro); cudaFree(c->orig_ci); cudaFree(c->row_ptr); cudaFree(c->col); cudaFree(c->new2old);
-  c->orig_ro = c->orig_ci = c->row_ptr = c->col = c->new2old = nullptr;
+  cudaFree(c->orig_ro); cudaFree(c->orig_ci); cudaFree(c->row_ptr); cudaFree(c->col); cudaFree(c->new2old); cudaFree(c->seg_store); cudaFree(c->sell_sp); cudaFree(c->sell_col);
+  c->orig_ro = c->orig_ci = c->row_ptr = c->col = c->new2old = c->seg_store = c->sell_sp = c->sell_col = nullptr;
+  c->n_long = c->n_items = 0; c->sell_entries = 0;
+  c->ncolblk = 1;
   c->n = c->nnz = c->n_loc = c->nnz_loc = 0;
 }
 
-static void make_plan(const uint32_t* bounds /* [5]: first row with len <= 32,16,8,4,2 */, uint32_t n_loc, lz_spmv_plan* plan) {
-  // len > 32 -> 32 lanes, (16,32] -> 16, (8,16] -> 8, (4,8] -> 4, (2,4] -> 2, <= 2 -> 1 lane per row
-  const uint32_t lg[6] = {5, 4, 3, 2, 1, 0};
-  uint32_t begin = 0, blocks = 0;
-  plan->nbins = 0;
-  for (int b = 0; b < 6; b++) {
-    uint32_t end = (b < 5) ? bounds[b] : n_loc;
-    if (end > begin) {
-      lz_spmv_bin& bin = plan->bin[plan->nbins++];
-      bin.row_begin = begin; bin.row_end = end; bin.log2_lanes = lg[b]; bin.block_begin = blocks;
-      uint64_t threads = (uint64_t)(end - begin) << lg[b];
-      blocks += (uint32_t)((threads + 255) / 256);
+// Row bins: local rows are sorted by total length (non-increasing); bounds[t] = first row with len <= kThr[t].
+// For each column block the lanes-per-row of a bin follow the bin's mean slice length in that block (any choice is
+// correct — the kernel loops over longer slices — it only has to keep lanes busy and slices coalesced).
+static const uint32_t kThr[7] = {128, 64, 32, 16, 8, 4, 2};
+static void make_plans(const uint32_t* bounds, uint32_t n_loc, uint32_t nblk, const unsigned long long* bin_blk_nnz /* [8][nblk] */,
+                       lz_spmv_plan* plans) {
+  for (uint32_t blk = 0; blk < nblk; blk++) {
+    lz_spmv_plan* plan = &plans[blk];
+    uint32_t begin = 0, items = 0;
+    plan->nbins = 0;
+    for (int b = 0; b < 8; b++) {
+      uint32_t end = (b < 7) ? bounds[b] : n_loc;
+      if (end > begin) {
+        const double mean = (double)bin_blk_nnz[b * nblk + blk] / (double)(end - begin);
+        uint16_t lg, per;
+        if (mean > 48.0) { lg = 5; per = 8; }
+        else {
+          per = 2;
+          lg = 0;
+          while (lg < 5 && (double)(2u << lg) < mean * 1.25) lg++;   // 2 * L >= 1.25 * mean slice length
+        }
+        lz_spmv_bin& bin = plan->bin[plan->nbins++];
+        bin.row_begin = begin; bin.row_end = end; bin.log2_lanes = lg; bin.per_lane = per; bin.item_begin = items;
+        const uint32_t rows_per_item = (LZ_SPMV_BLOCK >> lg) * LZ_SPMV_ROWS_PER_GROUP;
+        items += (end - begin + rows_per_item - 1) / rows_per_item;
+      }
+      begin = end;
     }
-    begin = end;
+    plan->nitems = items;
   }
-  plan->nblocks = blocks;
 }
 
 // Takes ownership of ro_d / ci_d (original-order CSR on the device).
@@ -214,40 +314,72 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
   }
   c->max_degree = ~kfirst;
 
-  // 4. local column lists in the new numbering, ascending within each row (one 64-bit radix sort)
+  // 4. column blocks: how many windows of x, so that one pass of the SpMV gathers from an L2-resident window
+  const uint64_t n_pad_ = n_loc * world;
+  uint64_t window = 64ull << 20;                       // bytes of x one pass may gather from
+  if (const char* e = getenv("LZ_SPMV_WINDOW_MB")) { long v = atol(e); if (v >= 1) window = (uint64_t)v << 20; }
+  uint32_t nblk = (uint32_t)((n_pad_ * 8 + window - 1) / window);
+  if (const char* e = getenv("LZ_SPMV_COLBLOCKS")) { int v = atoi(e); if (v >= 1) nblk = (uint32_t)v; }
+  if (nblk < 1) nblk = 1;
+  if (nblk > LZ_MAX_COLBLK) nblk = LZ_MAX_COLBLK;
+  const int rowbits = bits_for(n_loc);
+  while (nblk > 1 && 32 + rowbits + bits_for(nblk) > 64) nblk /= 2;
+  const uint64_t width = (n_pad_ + nblk - 1) / nblk;
+  c->ncolblk = nblk;
+
+  // 5. local column lists in the new numbering: column-block-major, row-major, ascending column (one 64-bit radix sort)
   {
     DevBuf k_in, k_out, t4; size_t b4 = 0;
     uint64_t m = c->nnz_loc;
     LZ_CUDA(cudaMalloc(&k_in.p, (m ? m : 1) * 8)); LZ_CUDA(cudaMalloc(&k_out.p, (m ? m : 1) * 8));
     LZ_CUDA(cudaMalloc((void**)&c->col, (m ? m : 1) * 4));
+    LZ_CUDA(cudaMalloc((void**)&c->seg_store, (uint64_t)nblk * (n_loc + 1) * 4));
     if (m) {
       k_local_keys<<<grid_for(n_loc * 32, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), ro_d, ci_d, old2new.as<uint32_t>(), c->row_ptr, n,
-                                                                world, rank, n_loc, k_in.as<uint64_t>());
-      int end_bit = 32 + bits_for(n_loc);
+                                                                world, rank, n_loc, width, rowbits, k_in.as<uint64_t>());
+      int end_bit = 32 + rowbits + (nblk > 1 ? bits_for(nblk) : 0);
+      if (end_bit > 64) end_bit = 64;
       LZ_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, b4, k_in.as<uint64_t>(), k_out.as<uint64_t>(), (int64_t)m, 0, end_bit, st));
       LZ_CUDA(cudaMalloc(&t4.p, b4 ? b4 : 1));
       LZ_CUDA(cub::DeviceRadixSort::SortKeys(t4.p, b4, k_in.as<uint64_t>(), k_out.as<uint64_t>(), (int64_t)m, 0, end_bit, st));
       k_low32<<<grid_for(m, 256), 256, 0, st>>>(k_out.as<uint64_t>(), m, c->col);
     }
+    k_block_row_ptr<<<grid_for((uint64_t)nblk * (n_loc + 1), 256), 256, 0, st>>>(k_out.as<uint64_t>(), m, n_loc, nblk, rowbits, c->seg_store);
     LZ_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t b = 0; b < nblk; b++) c->seg[b] = c->seg_store + (uint64_t)b * (n_loc + 1);
+    c->seg[nblk] = nullptr;
   }
 
-  // 5. SpMV plan from the (non-increasing) local row lengths
+  // 6. SpMV plans
   {
-    const uint32_t thr_h[6] = {32, 16, 8, 4, 2, 0};
-    DevBuf thr_d, out_d;
-    uint32_t out_h[6];
-    LZ_CUDA(cudaMalloc(&thr_d.p, sizeof(thr_h))); LZ_CUDA(cudaMalloc(&out_d.p, sizeof(out_h)));
-    LZ_CUDA(cudaMemcpyAsync(thr_d.p, thr_h, sizeof(thr_h), cudaMemcpyHostToDevice, st));
-    k_bin_bounds<<<1, 32, 0, st>>>(c->row_ptr, (uint32_t)n_loc, thr_d.as<uint32_t>(), 6, out_d.as<uint32_t>());
+    DevBuf thr_d, out_d, segp_d, binrows_d, cnt_d;
+    uint32_t out_h[7];
+    LZ_CUDA(cudaMalloc(&thr_d.p, sizeof(kThr))); LZ_CUDA(cudaMalloc(&out_d.p, sizeof(out_h)));
+    LZ_CUDA(cudaMemcpyAsync(thr_d.p, kThr, sizeof(kThr), cudaMemcpyHostToDevice, st));
+    k_bin_bounds<<<1, 32, 0, st>>>(c->row_ptr, (uint32_t)n_loc, thr_d.as<uint32_t>(), 7, out_d.as<uint32_t>());
     LZ_CUDA(cudaMemcpyAsync(out_h, out_d.p, sizeof(out_h), cudaMemcpyDeviceToHost, st));
     LZ_CUDA(cudaStreamSynchronize(st));
-    make_plan(out_h, (uint32_t)n_loc, &c->plan_auto);
+    uint32_t bin_rows[9];
+    bin_rows[0] = 0;
+    for (int b = 0; b < 7; b++) bin_rows[b + 1] = out_h[b];
+    bin_rows[8] = (uint32_t)n_loc;
+    std::vector<unsigned long long> cnt_h(8 * nblk);
+    LZ_CUDA(cudaMalloc(&segp_d.p, sizeof(uint32_t*) * (nblk + 1))); LZ_CUDA(cudaMalloc(&binrows_d.p, sizeof(bin_rows)));
+    LZ_CUDA(cudaMalloc(&cnt_d.p, 8 * nblk * sizeof(unsigned long long)));
+    LZ_CUDA(cudaMemcpyAsync(segp_d.p, c->seg, sizeof(uint32_t*) * (nblk + 1), cudaMemcpyHostToDevice, st));   // synchronous w.r.t. host memory: pageable source
+    LZ_CUDA(cudaMemcpyAsync(binrows_d.p, bin_rows, sizeof(bin_rows), cudaMemcpyHostToDevice, st));
+    k_bin_block_nnz<<<dim3(8, nblk), 256, 0, st>>>((const uint32_t* const*)segp_d.p, binrows_d.as<uint32_t>(), nblk,
+                                                    (unsigned long long*)cnt_d.p);
+    LZ_CUDA(cudaMemcpyAsync(cnt_h.data(), cnt_d.p, 8 * nblk * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    LZ_CUDA(cudaStreamSynchronize(st));
+    make_plans(out_h, (uint32_t)n_loc, nblk, cnt_h.data(), c->plan_auto);
     // warp-per-row for everything
     c->plan_warp.nbins = 1;
-    c->plan_warp.bin[0] = {0u, (uint32_t)n_loc, 5u, 0u};
-    c->plan_warp.nblocks = (uint32_t)((n_loc * 32 + 255) / 256);
-    c->plan = (c->spmv_variant == LZ_SPMV_WARP) ? c->plan_warp : c->plan_auto;
+    c->plan_warp.bin[0] = {0u, (uint32_t)n_loc, (uint16_t)5, (uint16_t)2, 0u};
+    {
+      const uint32_t rows_per_item = (LZ_SPMV_BLOCK >> 5) * LZ_SPMV_ROWS_PER_GROUP;
+      c->plan_warp.nitems = (uint32_t)((n_loc + rows_per_item - 1) / rows_per_item);
+    }
     // isolated vertices: local rows with length 0 start at out_h[5]; every rank sees ~1/world of them. Global count from the
     // sorted degree keys: positions s with deg == 0 are the tail; first such s = lower_bound over all ranks -> computed on rank-agnostic data:
     // empty_global = n - (#vertices with deg > 0). Use the degree keys (ascending ~deg): deg == 0 <=> key == 0xFFFFFFFF.
@@ -259,6 +391,45 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
     LZ_CUDA(cudaMalloc(&t5.p, b5 ? b5 : 1));
     LZ_CUDA(cub::DeviceReduce::Sum(t5.p, b5, it, cnt.as<uint64_t>(), (int64_t)n, st));
     LZ_CUDA(cudaMemcpyAsync(&c->empty_rows, cnt.p, 8, cudaMemcpyDeviceToHost, st));
+    LZ_CUDA(cudaStreamSynchronize(st));
+  }
+  // 7. sliced layout for the default SpMV
+  {
+    uint32_t n_long = 0;   // rows with total length > LZ_SELL_LONG (lengths are non-increasing): binary search on the device row_ptr
+    {
+      DevBuf thr_d, out_d;
+      const uint32_t thr = LZ_SELL_LONG;
+      LZ_CUDA(cudaMalloc(&thr_d.p, 4)); LZ_CUDA(cudaMalloc(&out_d.p, 4));
+      LZ_CUDA(cudaMemcpyAsync(thr_d.p, &thr, 4, cudaMemcpyHostToDevice, st));
+      k_bin_bounds<<<1, 32, 0, st>>>(c->row_ptr, (uint32_t)n_loc, thr_d.as<uint32_t>(), 1, out_d.as<uint32_t>());
+      LZ_CUDA(cudaMemcpyAsync(&n_long, out_d.p, 4, cudaMemcpyDeviceToHost, st));
+      LZ_CUDA(cudaStreamSynchronize(st));
+    }
+    const uint32_t n_items = n_long + (uint32_t)((n_loc - n_long + 31) / 32);
+    const uint64_t tot_items = (uint64_t)nblk * n_items;
+    c->n_long = n_long; c->n_items = n_items;
+    DevBuf widths, segp_d, t7, last2;
+    size_t b7 = 0;
+    LZ_CUDA(cudaMalloc(&widths.p, (tot_items + 1) * 4));
+    LZ_CUDA(cudaMalloc((void**)&c->sell_sp, (tot_items + 1) * 4));
+    LZ_CUDA(cudaMalloc(&segp_d.p, sizeof(uint32_t*) * (nblk + 1)));
+    LZ_CUDA(cudaMemcpy(segp_d.p, c->seg, sizeof(uint32_t*) * (nblk + 1), cudaMemcpyHostToDevice));
+    LZ_CUDA(cudaMemsetAsync(widths.as<uint32_t>() + tot_items, 0, 4, st));
+    k_sell_widths<<<grid_for(tot_items * 32, 256), 256, 0, st>>>((const uint32_t* const*)segp_d.p, nblk, n_long, n_items, (uint32_t)n_loc,
+                                                                  widths.as<uint32_t>());
+    LZ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b7, widths.as<uint32_t>(), c->sell_sp, (int64_t)(tot_items + 1), st));
+    LZ_CUDA(cudaMalloc(&t7.p, b7 ? b7 : 1));
+    LZ_CUDA(cub::DeviceScan::ExclusiveSum(t7.p, b7, widths.as<uint32_t>(), c->sell_sp, (int64_t)(tot_items + 1), st));
+    uint32_t total_chunks = 0;
+    LZ_CUDA(cudaMemcpyAsync(&total_chunks, c->sell_sp + tot_items, 4, cudaMemcpyDeviceToHost, st));
+    LZ_CUDA(cudaStreamSynchronize(st));
+    c->sell_entries = (uint64_t)total_chunks * 32;
+    if (c->sell_entries > 6 * c->nnz_loc + 64 * (uint64_t)tot_items + 1024)   // 32-bit chunk counter wrapped, or absurd padding
+      return lz_fail(LZ_ERR_ARG, "sliced layout too large (%llu entries for %llu non-zeros)", (unsigned long long)c->sell_entries,
+                     (unsigned long long)c->nnz_loc);
+    LZ_CUDA(cudaMalloc((void**)&c->sell_col, (c->sell_entries ? c->sell_entries : 1) * 4));
+    k_sell_fill<<<grid_for(tot_items * 32, 256), 256, 0, st>>>((const uint32_t* const*)segp_d.p, c->col, c->sell_sp, nblk, n_long, n_items,
+                                                                (uint32_t)n_loc, c->sell_col);
     LZ_CUDA(cudaStreamSynchronize(st));
   }
   LZ_CUDA(cudaGetLastError());

@@ -20,10 +20,11 @@
 #include "lz_ctx.h"
 
 #include <math.h>
+#include <string.h>
 
 namespace {
 
-constexpr int kBlock = 256;
+constexpr int kBlock = LZ_SPMV_BLOCK;
 constexpr int kWarps = kBlock / 32;
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -70,64 +71,206 @@ __device__ __forceinline__ void grid_sum_finish(double cta_val, double* partials
 }
 
 // ------------------------------------------------------------------------------------------------------------- SpMV
-// One row is served by L = 2^LG cooperating lanes. Local rows are sorted by length, so all rows of a bin have
-// len in (L, 2L] (or > 32 for L = 32): lanes of a warp run the same trip count and adjacent rows are adjacent in col[].
-template <int LG>
-__device__ __forceinline__ double spmv_rows(const lz_spmv_bin& bin, uint32_t blk, const uint32_t* __restrict__ rp,
-                                            const uint32_t* __restrict__ col, const double* __restrict__ x,
-                                            const double* __restrict__ q, double* __restrict__ w) {
+// Value-less CSR gather-sum. One row is served by L = 2^LG cooperating lanes ("vector per row"; L = 32 is warp per row).
+// Local rows are sorted by length, so every row of a bin has len in (L, 2L] (L = 1: len <= 2; L = 32: len > 32): all
+// lanes of a warp run the same trip count, and the rows a warp touches are adjacent in col[], so the index stream is
+// read in contiguous 128-byte pieces with streaming (evict-first) loads.
+//
+// The kernel is bound by the rate at which an SM's L1 can look up distinct 128-byte lines (one per clock: 275 G random
+// 8-byte gathers/s chip-wide, profiles/microbench/gather_bench_r01.txt), not by DRAM; what matters is keeping ~10^3
+// gathers in flight per SM. Each lane group therefore works on R rows at once: all 2R index loads are issued, then all
+// 2R gathers, then the sums — and CTAs are persistent (static item-stride loop), so the reduction tail is paid once.
+constexpr int kSpmvR = LZ_SPMV_ROWS_PER_GROUP;
+
+template <int LG, int PER>
+__device__ __forceinline__ double spmv_item(const lz_spmv_bin& bin, uint32_t item, const uint32_t* __restrict__ seg_lo,
+                                            const uint32_t* __restrict__ seg_hi, const uint32_t* __restrict__ col,
+                                            const double* __restrict__ x, const double* __restrict__ q, double* __restrict__ w,
+                                            bool accumulate, bool final_pass) {
   constexpr uint32_t L = 1u << LG;
-  const uint32_t t = blk * kBlock + threadIdx.x;
-  const uint32_t row = bin.row_begin + (t >> LG);
-  const uint32_t sub = t & (L - 1);
-  const bool valid = row < bin.row_end;
-  double sum = 0.0;
-  if (valid) {
-    uint32_t j = __ldg(rp + row) + sub;
-    const uint32_t e = __ldg(rp + row + 1);
-    // two independent gather chains per lane
-    double s1 = 0.0;
-    for (; j + L < e; j += 2 * L) {
-      const uint32_t c0 = __ldcs(col + j), c1 = __ldcs(col + j + L);
-      sum += __ldg(x + c0);
-      s1 += __ldg(x + c1);
-    }
-    if (j < e) sum += __ldg(x + __ldcs(col + j));
-    sum += s1;
-  }
+  constexpr uint32_t GROUPS = kBlock >> LG;
+  const uint32_t g = threadIdx.x >> LG, sub = threadIdx.x & (L - 1);
+  const uint32_t base = bin.row_begin + item * (GROUPS * kSpmvR) + g;
+  uint32_t b[kSpmvR], e[kSpmvR];
+  bool valid[kSpmvR];
 #pragma unroll
-  for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int r = 0; r < kSpmvR; r++) {
+    const uint32_t row = base + r * GROUPS;
+    valid[r] = row < bin.row_end;
+    b[r] = valid[r] ? __ldg(seg_lo + row) : 0u;
+    e[r] = valid[r] ? __ldg(seg_hi + row) : 0u;
+  }
+  double sum[kSpmvR];
+  constexpr bool kJoint = (PER * kSpmvR <= 8);   // short slices: first chunk of all R rows at once (PER*R loads in flight)
+  if constexpr (kJoint) {
+    uint32_t c[kSpmvR][PER];
+    bool p[kSpmvR][PER];
+#pragma unroll
+    for (int r = 0; r < kSpmvR; r++)
+#pragma unroll
+      for (int u = 0; u < PER; u++) {
+        const uint32_t j = b[r] + sub + u * L;
+        p[r][u] = j < e[r];
+        c[r][u] = p[r][u] ? __ldcs(col + j) : 0u;
+      }
+    double v[kSpmvR][PER];
+#pragma unroll
+    for (int r = 0; r < kSpmvR; r++)
+#pragma unroll
+      for (int u = 0; u < PER; u++) v[r][u] = p[r][u] ? __ldg(x + c[r][u]) : 0.0;
+#pragma unroll
+    for (int r = 0; r < kSpmvR; r++) {
+      double s = v[r][0];
+#pragma unroll
+      for (int u = 1; u < PER; u++) s += v[r][u];
+      sum[r] = s;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < kSpmvR; r++) sum[r] = 0.0;
+  }
+  // remaining chunks (all chunks for the long-slice variants), row by row, PER loads in flight
+#pragma unroll
+  for (int r = 0; r < kSpmvR; r++) {
+    for (uint32_t j0 = b[r] + sub + (kJoint ? PER * L : 0u); j0 < e[r]; j0 += PER * L) {
+      uint32_t cc[PER];
+#pragma unroll
+      for (int u = 0; u < PER; u++) cc[u] = (j0 + u * L < e[r]) ? __ldcs(col + j0 + u * L) : 0xFFFFFFFFu;
+      double vv[PER];
+#pragma unroll
+      for (int u = 0; u < PER; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? __ldg(x + cc[u]) : 0.0;
+      double s = 0.0;
+#pragma unroll
+      for (int u = 0; u < PER; u++) s += vv[u];
+      sum[r] += s;
+    }
+  }
   double d = 0.0;
-  if (valid && sub == 0) {
-    w[row] = sum;
-    d = sum * q[row];
+#pragma unroll
+  for (int r = 0; r < kSpmvR; r++) {
+    double s = sum[r];
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (valid[r] && sub == 0) {
+      const uint32_t row = base + r * GROUPS;
+      if (accumulate) {
+        if (final_pass || e[r] > b[r]) {
+          s += w[row];
+          w[row] = s;
+        }
+      } else {
+        w[row] = s;
+      }
+      if (final_pass) d += s * q[row];
+    }
   }
   return d;
 }
 
-__global__ void __launch_bounds__(kBlock) k_spmv_dot(const __grid_constant__ lz_spmv_plan plan, const uint32_t* __restrict__ rp,
-                                                     const uint32_t* __restrict__ col, const double* __restrict__ x,
-                                                     const double* __restrict__ q, double* __restrict__ w, double* partials,
-                                                     unsigned int* ticket, double* alpha_out) {
+// One pass = one column block. accumulate: w += (pass > 0). final_pass: also alpha partial = w . q and the grid reduction.
+__global__ void __launch_bounds__(kBlock) k_spmv_dot(const __grid_constant__ lz_spmv_plan plan, const uint32_t* __restrict__ seg_lo,
+                                                     const uint32_t* __restrict__ seg_hi, const uint32_t* __restrict__ col,
+                                                     const double* __restrict__ x, const double* __restrict__ q, double* __restrict__ w,
+                                                     double* partials, unsigned int* ticket, double* alpha_out, int accumulate,
+                                                     int final_pass) {
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
-  uint32_t b = 0;
+  double d = 0.0;
+  const bool acc = accumulate != 0, fin = final_pass != 0;
+  for (uint32_t item = blockIdx.x; item < plan.nitems; item += gridDim.x) {
+    uint32_t bi = 0;
 #pragma unroll
-  for (uint32_t i = 1; i < LZ_MAX_BINS; i++)
-    if (i < plan.nbins && blockIdx.x >= plan.bin[i].block_begin) b = i;
-  const lz_spmv_bin& bin = plan.bin[b];
-  const uint32_t blk = blockIdx.x - bin.block_begin;
-  double d;
-  switch (bin.log2_lanes) {
-    case 5: d = spmv_rows<5>(bin, blk, rp, col, x, q, w); break;
-    case 4: d = spmv_rows<4>(bin, blk, rp, col, x, q, w); break;
-    case 3: d = spmv_rows<3>(bin, blk, rp, col, x, q, w); break;
-    case 2: d = spmv_rows<2>(bin, blk, rp, col, x, q, w); break;
-    case 1: d = spmv_rows<1>(bin, blk, rp, col, x, q, w); break;
-    default: d = spmv_rows<0>(bin, blk, rp, col, x, q, w); break;
+    for (uint32_t i = 1; i < LZ_MAX_BINS; i++)
+      if (i < plan.nbins && item >= plan.bin[i].item_begin) bi = i;
+    const lz_spmv_bin& bin = plan.bin[bi];
+    const uint32_t it = item - bin.item_begin;
+#define LZ_SPMV_CASE(LG, PER) d += spmv_item<LG, PER>(bin, it, seg_lo, seg_hi, col, x, q, w, acc, fin)
+    switch (bin.log2_lanes) {
+      case 5:
+        if (bin.per_lane == 2) LZ_SPMV_CASE(5, 2);
+        else LZ_SPMV_CASE(5, 8);
+        break;
+      case 4: LZ_SPMV_CASE(4, 2); break;
+      case 3: LZ_SPMV_CASE(3, 2); break;
+      case 2: LZ_SPMV_CASE(2, 2); break;
+      case 1: LZ_SPMV_CASE(1, 2); break;
+      default: LZ_SPMV_CASE(0, 2); break;
+    }
+#undef LZ_SPMV_CASE
   }
-  d = block_sum(d, sm);
-  grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last);
+  if (fin) {
+    d = block_sum(d, sm);
+    grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- SpMV, sliced layout (default)
+// One warp per work item (lz_ctx.h): a long row read along the row, or 32 consecutive short rows read "one entry of every
+// row" at a time. Either way the index stream is consumed as whole 128-byte lines (one L1 wavefront per 32 gathers),
+// there are no per-row pointer loads and — for the short-row items, i.e. almost all of the matrix — no shuffles: the
+// gathers themselves are all that is left on the SM's load path, which is what bounds this kernel (1 line/clk/SM).
+constexpr int kSellU = 8;   // chunks (gathers per lane) in flight
+__global__ void __launch_bounds__(kBlock) k_spmv_sell(const uint32_t* __restrict__ sp, const uint32_t* __restrict__ scol, uint32_t n_long,
+                                                      uint32_t n_items, uint32_t n_loc, const double* __restrict__ x,
+                                                      const double* __restrict__ q, double* __restrict__ w, double* partials,
+                                                      unsigned int* ticket, double* alpha_out, int accumulate, int final_pass) {
+  __shared__ double sm[kWarps];
+  __shared__ bool s_last;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nwarps = gridDim.x * kWarps;
+  double d = 0.0;
+  for (uint32_t item = blockIdx.x * kWarps + (threadIdx.x >> 5); item < n_items; item += nwarps) {
+    const uint32_t c0 = __ldg(sp + item), nchunk = __ldg(sp + item + 1) - c0;
+    const uint32_t* p = scol + (uint64_t)c0 * 32 + lane;
+    double acc = 0.0;
+    uint32_t j = 0;
+    for (; j + kSellU <= nchunk; j += kSellU) {
+      uint32_t cc[kSellU];
+#pragma unroll
+      for (int u = 0; u < kSellU; u++) cc[u] = __ldcs(p + (uint64_t)(j + u) * 32);
+      double vv[kSellU];
+#pragma unroll
+      for (int u = 0; u < kSellU; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? __ldg(x + cc[u]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < kSellU; u++) acc += vv[u];
+    }
+    if (j < nchunk) {
+      const uint32_t rem = nchunk - j;
+      uint32_t cc[kSellU];
+#pragma unroll
+      for (int u = 0; u < kSellU - 1; u++) cc[u] = (u < (int)rem) ? __ldcs(p + (uint64_t)(j + u) * 32) : 0xFFFFFFFFu;
+      double vv[kSellU];
+#pragma unroll
+      for (int u = 0; u < kSellU - 1; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? __ldg(x + cc[u]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < kSellU - 1; u++) acc += vv[u];
+    }
+    uint32_t row;
+    bool writer;
+    if (item < n_long) {
+      acc = warp_sum(acc);
+      row = item;
+      writer = lane == 0;
+    } else {
+      row = n_long + (item - n_long) * 32 + lane;
+      writer = row < n_loc;
+    }
+    if (writer) {
+      if (accumulate) {
+        if (final_pass || nchunk) {
+          acc += w[row];
+          w[row] = acc;
+        }
+      } else {
+        w[row] = acc;
+      }
+      if (final_pass) d += acc * q[row];
+    }
+  }
+  if (final_pass) {
+    d = block_sum(d, sm);
+    grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last);
+  }
 }
 
 // --------------------------------------------------------------------------------------------- fused vector update
@@ -499,11 +642,27 @@ static int ensure_partials(lz_ctx* c, uint64_t count) {
 }
 
 int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out) {
-  const lz_spmv_plan& plan = c->plan;
-  if (plan.nblocks == 0) return lz_fail(LZ_ERR_ARG, "empty SpMV plan");
-  LZ_TRY(ensure_partials(c, plan.nblocks));
-  k_spmv_dot<<<plan.nblocks, kBlock, 0, c->stream>>>(plan, c->row_ptr, c->col, x_gather, q_local, w_out, c->partials, c->ticket + 0, alpha_out);
-  LZ_LAUNCH_CHECK();
+  for (uint32_t blk = 0; blk < c->ncolblk; blk++) {
+    const int acc = blk > 0, fin = blk + 1 == c->ncolblk;
+    if (c->spmv_variant == LZ_SPMV_AUTO) {          // sliced layout: long rows warp-per-row, short rows 32 per warp
+      uint32_t grid = (uint32_t)c->sm_count * c->spmv_ctas_per_sm;
+      const uint32_t need = (c->n_items + kWarps - 1) / kWarps;
+      if (grid > need) grid = need;
+      if (grid < 1) grid = 1;
+      LZ_TRY(ensure_partials(c, grid));
+      k_spmv_sell<<<grid, kBlock, 0, c->stream>>>(c->sell_sp + (uint64_t)blk * c->n_items, c->sell_col, c->n_long, c->n_items,
+                                                  (uint32_t)c->n_loc, x_gather, q_local, w_out, c->partials, c->ticket + 0, alpha_out, acc, fin);
+    } else {                                         // CSR: vector (sub-warp) per row by degree bin, or warp per row
+      const lz_spmv_plan& plan = (c->spmv_variant == LZ_SPMV_WARP) ? c->plan_warp : c->plan_auto[blk];
+      if (plan.nitems == 0) return lz_fail(LZ_ERR_ARG, "empty SpMV plan");
+      uint32_t grid = (uint32_t)c->sm_count * c->spmv_ctas_per_sm;
+      if (grid > plan.nitems) grid = plan.nitems;
+      LZ_TRY(ensure_partials(c, grid));
+      k_spmv_dot<<<grid, kBlock, 0, c->stream>>>(plan, c->seg[blk], c->seg[blk] + 1, c->col, x_gather, q_local, w_out, c->partials,
+                                                 c->ticket + 0, alpha_out, acc, fin);
+    }
+    LZ_LAUNCH_CHECK();
+  }
   return LZ_OK;
 }
 

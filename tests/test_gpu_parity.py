@@ -60,13 +60,13 @@ def test_full_reorth_within_tolerance_of_plain_reference(lz, orc, golden, ctx, n
     assert np.abs(Q @ Q.T - np.eye(k)).max() < 1e-12
 
 
-@pytest.mark.parametrize("variant", ["auto", "warp"])
+@pytest.mark.parametrize("variant", ["auto", "vector", "warp"])
 @pytest.mark.parametrize("spec_name", ["er", "rmat", "band", "tiny"])
 def test_spmv_bit_exact_on_integer_data(lz, orc, ctx, spec_name, variant):
     spec = {"er": lz.GraphSpec.er(30011, 150000, 5), "rmat": lz.GraphSpec.rmat(15, 8, 3),
             "band": lz.GraphSpec.band(20000, 9), "tiny": lz.GraphSpec.er(33, 40, 1)}[spec_name]
     n, ro, ci = lz.generate_host(spec)
-    ctx.set_spmv_variant(lz.SPMV_WARP if variant == "warp" else lz.SPMV_AUTO)
+    ctx.set_spmv_variant({"auto": lz.SPMV_AUTO, "vector": lz.SPMV_VECTOR, "warp": lz.SPMV_WARP}[variant])
     try:
         ctx.csr_upload(ro, ci)
         rng = np.random.default_rng(7)
