@@ -202,8 +202,9 @@ def main():
     uid = None
     if world > 1:
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # torch.distributed is host-side plumbing only (unique-id broadcast, barriers, max over ranks): gloo suffices.
+        # The data path's collectives are NCCL calls inside liblzb200.so on its own communicator.
+        dist.init_process_group("gloo")
         box = [lz.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         uid = box[0]
@@ -215,7 +216,7 @@ def main():
     def max_over_ranks(x):
         if not dist:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        t = torch.tensor([x], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 

@@ -27,6 +27,7 @@ const lz_nccl_api* lz_nccl() {
   api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
   api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
   api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+  api.CommAbort = (decltype(api.CommAbort))sym("ncclCommAbort");
   api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
   api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
   api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
@@ -194,8 +195,9 @@ extern "C" int lz_create_dist(int device, int rank, int world, const void* uid, 
 extern "C" int lz_destroy(lz_ctx* c) {
   if (!c) return LZ_OK;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  if (c->comm && lz_nccl()) lz_nccl()->CommDestroy(c->comm);
+  const bool healthy = cudaStreamSynchronize(c->stream) == cudaSuccess;
+  // after a device fault a collective may never complete on the peers: abort instead of the (blocking) destroy
+  if (c->comm && lz_nccl()) { if (healthy) lz_nccl()->CommDestroy(c->comm); else lz_nccl()->CommAbort(c->comm); }
   free_vectors(c);
   lz_free_graph(c);
   cudaFree(c->scal); cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->status); cudaFree(c->flush_buf);

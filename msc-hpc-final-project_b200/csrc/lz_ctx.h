@@ -18,6 +18,7 @@ struct lz_nccl_api {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*);
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
   ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*CommAbort)(ncclComm_t);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
   const char* (*GetErrorString)(ncclResult_t);
@@ -67,7 +68,7 @@ struct lz_ctx {
 
   // ---- graph ------------------------------------------------------------------------------------------------------
   uint64_t n = 0, nnz = 0;         // global
-  uint64_t n_loc = 0;              // rows per rank = ceil(n / world); global padded length = n_loc * world
+  uint64_t n_loc = 0;              // rows per rank = ceil(n / world) rounded up to 32; global padded length = n_loc * world
   uint64_t nnz_loc = 0;
   uint64_t ldv = 0;                // leading dimension of V (n_loc rounded up to 32 doubles => 256-byte aligned rows)
   uint32_t max_degree = 0;

@@ -256,7 +256,8 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
   c->orig_ro = ro_d; c->orig_ci = ci_d;
   c->n = n; c->nnz = nnz;
   const uint32_t world = (uint32_t)c->world, rank = (uint32_t)c->rank;
-  const uint64_t n_loc = (n + world - 1) / world, n_pad = n_loc * world;
+  // rows per rank, rounded up to 32 so every rank's slice of the gathered vector starts 256-byte aligned (vector loads/stores)
+  const uint64_t n_loc = (((n + world - 1) / world) + 31) & ~31ull, n_pad = n_loc * world;
   if (n_pad > 0xFFFFFFFEull) return lz_fail(LZ_ERR_ARG, "n = %llu too large for 32-bit vertex ids", (unsigned long long)n);
   c->n_loc = n_loc;
   cudaStream_t st = c->stream;

@@ -1,0 +1,70 @@
+"""Multi-GPU parity check, one process per GPU:  torchrun --nproc-per-node P tests/dist_check.py
+Every rank uploads the same CSR, keeps its row shard, and must reproduce the reference's golden e^A·x (and the single-GPU
+answer on a generated graph) through the NCCL all-gather / all-reduce path. Prints 'DIST_OK <world>' on rank 0."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import __graft_entry__ as g  # noqa: E402
+import oracle as orc  # noqa: E402
+
+
+def rel2(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def main():
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    dist.init_process_group("gloo")
+    lz = g.load_package()
+    box = [lz.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx = lz.Context(local, rank, world, box[0])
+    gdir = os.path.join(ROOT, "tests", "golden")
+    for name in ("er_n257_k10_ragged", "rmat_s12_k30", "c1_er_n10000_k20", "band_n4096_k40"):
+        gl = np.load(os.path.join(gdir, name + ".npz"))
+        ro, ci, k, n = gl["row_offset"], gl["col_idx"], int(gl["k"]), int(gl["n"])
+        if os.environ.get("LZ_DIST_VERBOSE"):
+            print(f"[rank {rank}] {name}", flush=True)
+        ctx.csr_upload(ro, ci)
+        gi = ctx.graph_info()
+        assert gi.n_local == (((n + world - 1) // world) + 31) // 32 * 32
+        y = ctx.expv_host(None, k)
+        if os.environ.get("LZ_DIST_VERBOSE"):
+            print(f"[rank {rank}] {name} expv done rel={rel2(y, gl['ans']):.2e}", flush=True)
+        assert rel2(y, gl["ans"]) < 1e-9, (name, rel2(y, gl["ans"]))
+        assert np.array_equal(orc.top_k(y), orc.top_k(gl["ans"])), name
+        y2 = ctx.expv_host(gl["x_random"], k)
+        assert rel2(y2, gl["ans_random"]) < 1e-9, name
+        yr = ctx.expv_host(None, k, lz.REORTH_FULL)
+        assert rel2(yr, gl["ans"]) < 1e-9, name
+        x = np.random.default_rng(5).integers(-1000, 1000, n).astype(np.float64)
+        assert np.array_equal(ctx.spmv_host(x), orc.spmv(ro, ci, x)), name
+        q3 = ctx.get_basis(min(3, k - 1))
+        assert abs(q3 @ q3 - 1) < 1e-12
+    # generated graph, compared with the CPU oracle
+    spec = lz.GraphSpec.rmat(16, 8, 1)
+    ctx.graph_generate(spec)
+    ro, ci = ctx.csr_download()
+    n = len(ro) - 1
+    y = ctx.expv_host(None, 30)
+    ref, _, _ = orc.expv(ro, ci, 30, np.ones(n))
+    assert rel2(y, ref) < 1e-9 and np.array_equal(orc.top_k(y), orc.top_k(ref))
+    # every rank holds the same answer bit for bit
+    ys = [None] * world
+    dist.all_gather_object(ys, y.tobytes())
+    assert all(b == ys[0] for b in ys)
+    ctx.close()
+    dist.barrier()
+    if rank == 0:
+        print(f"DIST_OK {world}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
