@@ -69,6 +69,11 @@ int lz_graph_generate_host(const lz_graph_spec* spec, uint64_t* n_out, uint64_t*
                            uint32_t** row_offset_out, uint32_t** col_idx_out);
 void lz_free_host(void* p);
 
+/* Edge list (0-based endpoints, any order, duplicates / both orientations / self loops allowed) -> symmetric simple CSR.
+ * What adjMatrix::populate_sparse_matrix does after parsing (adjMatrix.cc:36-44), without the std::set. */
+int lz_csr_from_edges(uint64_t n, uint64_t n_edges, const uint32_t* u, const uint32_t* v, uint64_t* nnz_out,
+                      uint32_t** row_offset_out, uint32_t** col_idx_out);
+
 /* Reference text format ("n n E" header, then E lines "col row", 1-based, upper-triangle entries once):
  * adjMatrix::populate_sparse_matrix (parallel-final/lib/adjMatrix.cc:21-46) and write_matrix_to_file (:53-69). */
 int lz_csr_read_text(const char* path, uint64_t* n_out, uint64_t* nnz_out, uint32_t** row_offset_out, uint32_t** col_idx_out);

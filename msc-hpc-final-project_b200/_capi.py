@@ -71,6 +71,7 @@ _sig("lz_last_error", restype=C.c_char_p)
 _sig("lz_version")
 _sig("lz_free_host", C.c_void_p, restype=None)
 _sig("lz_graph_generate_host", _P(GraphSpec), _u64p, _u64p, _P(_u32p), _P(_u32p))
+_sig("lz_csr_from_edges", C.c_uint64, C.c_uint64, _u32p, _u32p, _u64p, _P(_u32p), _P(_u32p))
 _sig("lz_csr_read_text", C.c_char_p, _u64p, _u64p, _P(_u32p), _P(_u32p))
 _sig("lz_csr_write_text", C.c_char_p, C.c_uint64, _u32p, _u32p)
 _sig("lz_csr_read_bin", C.c_char_p, _u64p, _u64p, _P(_u32p), _P(_u32p))
@@ -141,6 +142,13 @@ def generate_host(spec):
     n, nnz, ro, ci = C.c_uint64(), C.c_uint64(), _u32p(), _u32p()
     _check(lib.lz_graph_generate_host(C.byref(spec), C.byref(n), C.byref(nnz), C.byref(ro), C.byref(ci)))
     return _take_csr(n, nnz, ro, ci)
+
+
+def csr_from_edges(n, u, v):
+    u, v = np.ascontiguousarray(u, np.uint32), np.ascontiguousarray(v, np.uint32)
+    nnz, ro, ci = C.c_uint64(), _u32p(), _u32p()
+    _check(lib.lz_csr_from_edges(n, len(u), _u32(u), _u32(v), C.byref(nnz), C.byref(ro), C.byref(ci)))
+    return _take_csr(C.c_uint64(n), nnz, ro, ci)
 
 
 def read_text(path):

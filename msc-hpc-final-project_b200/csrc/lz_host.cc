@@ -61,6 +61,21 @@ extern "C" int lz_graph_generate_host(const lz_graph_spec* spec, uint64_t* n_out
   return lz_build_csr_from_keys(p.n, keys.data(), keys.size(), nnz_out, row_offset_out, col_idx_out);
 }
 
+extern "C" int lz_csr_from_edges(uint64_t n, uint64_t n_edges, const uint32_t* u, const uint32_t* v, uint64_t* nnz_out,
+                                 uint32_t** row_offset_out, uint32_t** col_idx_out) {
+  if (!nnz_out || !row_offset_out || !col_idx_out || (n_edges && (!u || !v))) return lz_fail(LZ_ERR_ARG, "null argument");
+  if (n == 0 || n > 0xFFFFFFFFull) return lz_fail(LZ_ERR_ARG, "bad vertex count %llu", (unsigned long long)n);
+  std::vector<uint64_t> keys;
+  keys.reserve(2 * n_edges);
+  for (uint64_t i = 0; i < n_edges; i++) {
+    if (u[i] >= n || v[i] >= n) return lz_fail(LZ_ERR_ARG, "edge %llu has a vertex out of range", (unsigned long long)i);
+    if (u[i] == v[i]) continue;
+    keys.push_back(((uint64_t)u[i] << 32) | v[i]);
+    keys.push_back(((uint64_t)v[i] << 32) | u[i]);
+  }
+  return lz_build_csr_from_keys(n, keys.data(), keys.size(), nnz_out, row_offset_out, col_idx_out);
+}
+
 extern "C" int lz_csr_read_text(const char* path, uint64_t* n_out, uint64_t* nnz_out, uint32_t** row_offset_out,
                                 uint32_t** col_idx_out) {
   if (!path || !n_out || !nnz_out || !row_offset_out || !col_idx_out) return lz_fail(LZ_ERR_ARG, "null argument");

@@ -253,3 +253,26 @@ def test_full_size_properties_c3(lz, orc, ctx):
     assert rel2(y50r, y50) < TOL and np.array_equal(orc.top_k(y50r), orc.top_k(y50))
     qa, qb = ctx.get_basis(49), ctx.get_basis(3)
     assert abs(qa @ qb) < 1e-12 and abs(qa @ qa - 1) < 1e-12
+
+
+def test_cpp_api_driver_matches_reference_golden(lz, golden, tmp_path):
+    """The C++ mirror of the reference API (lib/final: adjMatrix -> lanczosDecomp -> eigenDecomp -> multOut) reproduces the
+    reference's answer through the reference's own text format."""
+    import os
+    import subprocess
+    libdir = os.path.join(os.path.dirname(lz.lib_path), "..", "lib")
+    subprocess.check_call(["make", "-s", "-C", libdir])
+    g = golden("rmat_s12_k30")
+    mtx, ans, out = str(tmp_path / "g.mtx"), str(tmp_path / "ans.f64"), str(tmp_path / "out.txt")
+    lz.write_text(mtx, g["row_offset"], g["col_idx"])
+    g["ans"].astype(np.float64).tofile(ans)
+    r = subprocess.run([os.path.join(libdir, "final"), "--path", mtx, "-k", str(int(g["k"])), "--check", ans, "--write", out],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Relative norm of differences" in r.stdout
+    y = np.loadtxt(out)
+    assert np.linalg.norm(y - g["ans"]) / np.linalg.norm(g["ans"]) < TOL
+    # generated graph + reorth + Barabasi-Albert constructor paths run and give finite answers
+    for extra in (["--graph", "rmat", "--scale", "14", "-k", "20", "--reorth"], ["--graph", "ba", "-n", "5000", "-b", "4", "-k", "8"]):
+        r = subprocess.run([os.path.join(libdir, "final")] + extra, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "result finite: yes" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
