@@ -28,6 +28,7 @@ const lz_nccl_api* lz_nccl() {
   api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
   api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
   api.CommAbort = (decltype(api.CommAbort))sym("ncclCommAbort");
+  api.CommSplit = (decltype(api.CommSplit))dlsym(h, "ncclCommSplit");   // optional
   api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
   api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
   api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
@@ -122,10 +123,32 @@ int allreduce_sum(lz_ctx* c, double* buf, size_t count) {
   LZ_NCCL(lz_nccl()->AllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->stream));
   return LZ_OK;
 }
-int allgather_inplace(lz_ctx* c, double* full) {
+// All-gather of the chunk-major vector `full` (every rank has already stored its own slots). One in-place ncclAllGather
+// per chunk. async: issued on the communication stream behind `stream`, one event per chunk, so SpMV pass b can start as
+// soon as chunk b has arrived while later chunks are still in flight. Otherwise: on `stream`, fully ordered.
+int allgather_chunks(lz_ctx* c, double* full, bool async) {
   if (c->world == 1) return LZ_OK;
-  Scope s(c, 2);
-  LZ_NCCL(lz_nccl()->AllGather(full + (uint64_t)c->rank * c->n_loc, full, c->n_loc, ncclDouble, c->comm, c->stream));
+  const uint64_t cl = c->chunk_rows, span = cl * (uint64_t)c->world;
+  if (async && c->comm_overlap) {
+    LZ_CUDA(cudaEventRecord(c->ev_scaled, c->stream));
+    LZ_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_scaled, 0));
+    cudaEvent_t a = nullptr;
+    if (c->profiling) { a = next_event(c); cudaEventRecord(a, c->comm_stream); }
+    for (uint32_t b = 0; b < c->ncolblk; b++) {
+      double* base = full + (uint64_t)b * span;
+      LZ_NCCL(lz_nccl()->AllGather(base + (uint64_t)c->rank * cl, base, cl, ncclDouble, c->comm_ag, c->comm_stream));
+      LZ_CUDA(cudaEventRecord(c->ev_chunk[b], c->comm_stream));
+    }
+    if (c->profiling) { cudaEvent_t e = next_event(c); cudaEventRecord(e, c->comm_stream); g_marks.push_back({2, a, e}); }
+    c->chunks_in_flight = true;
+  } else {
+    Scope s(c, 2);
+    for (uint32_t b = 0; b < c->ncolblk; b++) {
+      double* base = full + (uint64_t)b * span;
+      LZ_NCCL(lz_nccl()->AllGather(base + (uint64_t)c->rank * cl, base, cl, ncclDouble, c->comm, c->stream));
+    }
+    c->chunks_in_flight = false;
+  }
   return LZ_OK;
 }
 
@@ -172,6 +195,13 @@ static int create_common(int device, int rank, int world, const void* uid, lz_ct
     memcpy(&id, uid, sizeof(id));
     if (!lz_nccl()) return LZ_ERR_NCCL;
     LZ_NCCL(lz_nccl()->CommInitRank(&c->comm, world, id, rank));
+    if (const char* e = getenv("LZ_COMM_OVERLAP")) c->comm_overlap = atoi(e) != 0;
+    // a second communicator so the chunked all-gather (communication stream) never serialises with the all-reduces
+    if (c->comm_overlap && lz_nccl()->CommSplit && lz_nccl()->CommSplit(c->comm, 0, rank, &c->comm_ag, nullptr) != ncclSuccess) c->comm_ag = nullptr;
+    if (!c->comm_ag) c->comm_overlap = false;
+    LZ_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    LZ_CUDA(cudaEventCreateWithFlags(&c->ev_scaled, cudaEventDisableTiming));
+    for (int b = 0; b < LZ_MAX_COLBLK; b++) LZ_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[b], cudaEventDisableTiming));
   }
   *out = c;
   return LZ_OK;
@@ -197,7 +227,12 @@ extern "C" int lz_destroy(lz_ctx* c) {
   cudaSetDevice(c->device);
   const bool healthy = cudaStreamSynchronize(c->stream) == cudaSuccess;
   // after a device fault a collective may never complete on the peers: abort instead of the (blocking) destroy
+  if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+  if (c->comm_ag && lz_nccl()) { if (healthy) lz_nccl()->CommDestroy(c->comm_ag); else lz_nccl()->CommAbort(c->comm_ag); }
   if (c->comm && lz_nccl()) { if (healthy) lz_nccl()->CommDestroy(c->comm); else lz_nccl()->CommAbort(c->comm); }
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->ev_scaled) cudaEventDestroy(c->ev_scaled);
+  for (int b = 0; b < LZ_MAX_COLBLK; b++) if (c->ev_chunk[b]) cudaEventDestroy(c->ev_chunk[b]);
   free_vectors(c);
   lz_free_graph(c);
   cudaFree(c->scal); cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->status); cudaFree(c->flush_buf);
@@ -235,8 +270,8 @@ extern "C" int lz_set_start_vector(lz_ctx* c, const double* x_host) {
   }
   LZ_TRY(lz_k_norm2(c, c->xstage, c->n, c->scal + 2));
   if (c->world > 1) {
-    LZ_TRY(lz_k_permute_in(c, c->xstage, c->scal + 2, 0, c->n_loc * (uint64_t)c->world, c->xfull));
-    LZ_CUDA(cudaMemcpyAsync(c->V, c->xfull + (uint64_t)c->rank * c->n_loc, c->n_loc * 8, cudaMemcpyDeviceToDevice, c->stream));
+    LZ_TRY(lz_k_permute_in(c, c->xstage, c->scal + 2, 0, c->n_loc * (uint64_t)c->world, c->xfull));   // every rank has all of x
+    LZ_TRY(lz_k_collect(c, c->xfull, c->V));
   } else {
     LZ_TRY(lz_k_permute_in(c, c->xstage, c->scal + 2, 0, c->n_loc, c->V));
   }
@@ -258,8 +293,8 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
   g_marks.clear();
   LZ_CUDA(cudaEventRecord(c->ev_a, c->stream));
   if (dist) {   // q_0 into the gathered buffer (a previous run left q_{k-1} there)
-    LZ_CUDA(cudaMemcpyAsync(c->xfull + (uint64_t)c->rank * c->n_loc, c->V, c->n_loc * 8, cudaMemcpyDeviceToDevice, c->stream));
-    LZ_TRY(allgather_inplace(c, c->xfull));
+    LZ_TRY(lz_k_spread(c, c->V, c->xfull));
+    LZ_TRY(allgather_chunks(c, c->xfull, true));
   }
   for (uint32_t j = 0; j < k; j++) {
     double* qj = c->V + (uint64_t)j * ldv;
@@ -285,9 +320,9 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
     LZ_TRY(allreduce_sum(c, c->scal + 1, 1));
     {  // beta_j = ||w|| ; q_{j+1} = w / beta_j                            (cu_lanczos.cu:120-123)
       Scope s(c, 1);
-      LZ_TRY(lz_k_scale(c, c->w, c->scal + 1, qj + ldv, dist ? c->xfull + (uint64_t)c->rank * c->n_loc : nullptr, c->beta + j));
+      LZ_TRY(lz_k_scale(c, c->w, c->scal + 1, qj + ldv, dist ? c->xfull : nullptr, c->beta + j));
     }
-    LZ_TRY(allgather_inplace(c, c->xfull));
+    LZ_TRY(allgather_chunks(c, c->xfull, true));
   }
   LZ_CUDA(cudaEventRecord(c->ev_b, c->stream));
   c->k_done = k;
@@ -354,8 +389,8 @@ static int gather_to_host(lz_ctx* c, const double* local, double* host_out) {
   // local [n_loc] (new order, this rank's slice) -> host [n] original order, on every rank
   const double* full = local;
   if (c->world > 1) {
-    LZ_CUDA(cudaMemcpyAsync(c->xfull + (uint64_t)c->rank * c->n_loc, local, c->n_loc * 8, cudaMemcpyDeviceToDevice, c->stream));
-    LZ_NCCL(lz_nccl()->AllGather(c->xfull + (uint64_t)c->rank * c->n_loc, c->xfull, c->n_loc, ncclDouble, c->comm, c->stream));
+    LZ_TRY(lz_k_spread(c, local, c->xfull));
+    LZ_TRY(allgather_chunks(c, c->xfull, false));
     full = c->xfull;
   }
   LZ_TRY(lz_k_permute_out(c, full, c->xstage));

@@ -19,6 +19,7 @@ struct lz_nccl_api {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
   ncclResult_t (*CommDestroy)(ncclComm_t);
   ncclResult_t (*CommAbort)(ncclComm_t);
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*);   // may be null (NCCL < 2.18)
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
   const char* (*GetErrorString)(ncclResult_t);
@@ -59,8 +60,12 @@ struct lz_spmv_plan {
 struct lz_ctx {
   int device = 0, rank = 0, world = 1;
   int sm_count = 148;
-  ncclComm_t comm = nullptr;
-  cudaStream_t stream = nullptr;
+  ncclComm_t comm = nullptr;       // scalar / coefficient all-reduces, on `stream`
+  ncclComm_t comm_ag = nullptr;    // chunked all-gather of the Krylov vector, on `comm_stream` (overlaps the SpMV passes)
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_scaled = nullptr, ev_chunk[LZ_MAX_COLBLK] = {};
+  bool comm_overlap = true;
+  bool chunks_in_flight = false;   // ev_chunk[] were recorded for the vector the next SpMV gathers from
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;      // lz_lanczos_run
   cudaEvent_t ev_e0 = nullptr, ev_e1 = nullptr;    // lz_tridiag_expv
   cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;    // lz_multout
@@ -68,8 +73,9 @@ struct lz_ctx {
 
   // ---- graph ------------------------------------------------------------------------------------------------------
   uint64_t n = 0, nnz = 0;         // global
-  uint64_t n_loc = 0;              // rows per rank = ceil(n / world) rounded up to 32; global padded length = n_loc * world
+  uint64_t n_loc = 0;              // rows per rank (>= ceil(n / world), multiple of chunk_rows); padded length = n_loc * world
   uint64_t nnz_loc = 0;
+  uint64_t chunk_rows = 0;         // cl: rows of each rank per column block; n_loc = ncolblk * cl
   uint64_t ldv = 0;                // leading dimension of V (n_loc rounded up to 32 doubles => 256-byte aligned rows)
   uint32_t max_degree = 0;
   uint64_t empty_rows = 0;
@@ -140,7 +146,11 @@ void lz_free_graph(lz_ctx* c);
 int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out /* device scalar or null */);
 int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev, const double* alpha, const double* beta_prev,
                      double* norm2_out /* device scalar or null */);
-int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* q_next_copy, double* beta_out);
+// q_next = w / sqrt(*norm2); when xfull != null also stores it into this rank's slots of the chunk-major gathered vector
+int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* xfull, double* beta_out);
+// local vector <-> this rank's slots of the chunk-major gathered vector
+int lz_k_spread(lz_ctx* c, const double* local, double* xfull);
+int lz_k_collect(lz_ctx* c, const double* xfull, double* local);
 int lz_k_norm2(lz_ctx* c, const double* v, uint64_t len, double* out);
 int lz_k_multidot(lz_ctx* c, const double* V, uint32_t nvec, const double* w, double* h_out /* device [nvec] */);
 int lz_k_combine(lz_ctx* c, const double* V, uint32_t nvec, const double* coef, double coef_sign, const double* base, double* out,

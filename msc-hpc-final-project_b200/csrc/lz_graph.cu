@@ -63,13 +63,16 @@ __global__ void k_fill_u32(uint32_t* p, uint64_t n, uint32_t v) {
   if (i < n) p[i] = v;
 }
 
-// sorted position s -> new id; builds old2new and new2old
-__global__ void k_relabel(const uint32_t* __restrict__ sorted_old, uint64_t n, uint32_t world, uint64_t n_loc,
+// sorted position s -> new id; builds old2new and new2old. Rank = s % world, local row l = s / world; the global
+// numbering is chunk-major: id = (l / cl) * (world * cl) + rank * cl + (l % cl), so chunk c of every rank's rows forms
+// one contiguous window of the gathered vector (= one column block = one piece of the pipelined all-gather).
+__global__ void k_relabel(const uint32_t* __restrict__ sorted_old, uint64_t n, uint32_t world, uint64_t cl,
                           uint32_t* __restrict__ old2new, uint32_t* __restrict__ new2old) {
   uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   uint32_t old = sorted_old[s];
-  uint32_t nw = (uint32_t)((s % world) * n_loc + s / world);
+  const uint64_t r = s % world, l = s / world;
+  uint32_t nw = (uint32_t)((l / cl) * (world * cl) + r * cl + (l % cl));
   old2new[old] = nw;
   new2old[nw] = old;
 }
@@ -256,8 +259,21 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
   c->orig_ro = ro_d; c->orig_ci = ci_d;
   c->n = n; c->nnz = nnz;
   const uint32_t world = (uint32_t)c->world, rank = (uint32_t)c->rank;
-  // rows per rank, rounded up to 32 so every rank's slice of the gathered vector starts 256-byte aligned (vector loads/stores)
-  const uint64_t n_loc = (((n + world - 1) / world) + 31) & ~31ull, n_pad = n_loc * world;
+  // Rows per rank and column blocks. A column block (= chunk) is `cl` rows of every rank: a window of world * cl
+  // entries of the gathered vector that one SpMV pass gathers from; it is sized to stay L2-resident (64 MiB measured
+  // best on C3, profiles/), and for world > 1 it is also the unit of the pipelined all-gather.
+  uint64_t window = 64ull << 20;
+  if (const char* e = getenv("LZ_SPMV_WINDOW_MB")) { long v = atol(e); if (v >= 1) window = (uint64_t)v << 20; }
+  const uint64_t rows32 = (((n + world - 1) / world) + 31) & ~31ull;
+  uint64_t cl = (window / 8 / world) & ~31ull;
+  if (cl < 32) cl = 32;
+  if (const char* e = getenv("LZ_SPMV_COLBLOCKS")) { int v = atoi(e); if (v >= 1) cl = (((rows32 + v - 1) / v) + 31) & ~31ull; }
+  if (cl > rows32) cl = rows32;
+  uint32_t nblk = (uint32_t)((rows32 + cl - 1) / cl);
+  if (nblk > LZ_MAX_COLBLK) { cl = (((rows32 + LZ_MAX_COLBLK - 1) / LZ_MAX_COLBLK) + 31) & ~31ull; nblk = (uint32_t)((rows32 + cl - 1) / cl); }
+  while (nblk > 1 && 32 + bits_for((uint64_t)nblk * cl) + bits_for(nblk) > 64) { cl *= 2; nblk = (uint32_t)((rows32 + cl - 1) / cl); }
+  const uint64_t n_loc = (uint64_t)nblk * cl, n_pad = n_loc * world;
+  c->chunk_rows = cl;
   if (n_pad > 0xFFFFFFFEull) return lz_fail(LZ_ERR_ARG, "n = %llu too large for 32-bit vertex ids", (unsigned long long)n);
   c->n_loc = n_loc;
   cudaStream_t st = c->stream;
@@ -283,7 +299,7 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
 
   // 2. relabel
   k_fill_u32<<<grid_for(n_pad, 256), 256, 0, st>>>(c->new2old, n_pad, 0xFFFFFFFFu);
-  k_relabel<<<grid_for(n, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), n, world, n_loc, old2new.as<uint32_t>(), c->new2old);
+  k_relabel<<<grid_for(n, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), n, world, cl, old2new.as<uint32_t>(), c->new2old);
 
   // 3. local row pointer
   k_local_lengths<<<grid_for(n_loc, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), ro_d, n, world, rank, n_loc, len.as<uint32_t>());
@@ -315,17 +331,9 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
   }
   c->max_degree = ~kfirst;
 
-  // 4. column blocks: how many windows of x, so that one pass of the SpMV gathers from an L2-resident window
-  const uint64_t n_pad_ = n_loc * world;
-  uint64_t window = 64ull << 20;                       // bytes of x one pass may gather from
-  if (const char* e = getenv("LZ_SPMV_WINDOW_MB")) { long v = atol(e); if (v >= 1) window = (uint64_t)v << 20; }
-  uint32_t nblk = (uint32_t)((n_pad_ * 8 + window - 1) / window);
-  if (const char* e = getenv("LZ_SPMV_COLBLOCKS")) { int v = atoi(e); if (v >= 1) nblk = (uint32_t)v; }
-  if (nblk < 1) nblk = 1;
-  if (nblk > LZ_MAX_COLBLK) nblk = LZ_MAX_COLBLK;
+  // 4. column blocks were fixed above (nblk windows of world * cl entries)
   const int rowbits = bits_for(n_loc);
-  while (nblk > 1 && 32 + rowbits + bits_for(nblk) > 64) nblk /= 2;
-  const uint64_t width = (n_pad_ + nblk - 1) / nblk;
+  const uint64_t width = (uint64_t)world * cl;
   c->ncolblk = nblk;
 
   // 5. local column lists in the new numbering: column-block-major, row-major, ascending column (one 64-bit radix sort)

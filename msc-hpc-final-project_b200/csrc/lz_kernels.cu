@@ -311,26 +311,39 @@ __global__ void __launch_bounds__(kBlock) k_update_norm(double* __restrict__ w, 
   if (norm2_out) grid_sum_finish(acc, partials, ticket, norm2_out, sm, &s_last);
 }
 
-// q_next = w / sqrt(norm2)  (true division, as cu_dvexda); optional second copy into the all-gather buffer; beta_out = sqrt(norm2)
+// Index of local row l in the chunk-major gathered vector (see k_relabel in lz_graph.cu).
+__device__ __forceinline__ uint64_t xfull_index(uint64_t l, uint64_t cl, uint32_t world, uint32_t rank) {
+  const uint64_t c = l / cl;
+  return c * (world * cl) + rank * cl + (l - c * cl);
+}
+
+// q_next = w / sqrt(norm2)  (true division, as cu_dvexda); optional second copy into this rank's slots of the gathered
+// vector; beta_out = sqrt(norm2). n and cl are even, so a double2 never straddles a chunk.
 __global__ void __launch_bounds__(kBlock) k_scale(const double* __restrict__ w, const double* __restrict__ norm2_p, uint64_t n,
-                                                  double* __restrict__ q_next, double* __restrict__ q_copy, double* beta_out) {
+                                                  double* __restrict__ q_next, double* __restrict__ xfull, uint64_t cl, uint32_t world,
+                                                  uint32_t rank, double* beta_out) {
   const double beta = sqrt(*norm2_p);
   if (blockIdx.x == 0 && threadIdx.x == 0 && beta_out) *beta_out = beta;
   const uint64_t n2 = n >> 1;
   const double2* w2 = reinterpret_cast<const double2*>(w);
   double2* q2 = reinterpret_cast<double2*>(q_next);
-  double2* c2 = reinterpret_cast<double2*>(q_copy);
   for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
     double2 v = w2[i];
     v.x /= beta;
     v.y /= beta;
     q2[i] = v;
-    if (q_copy) c2[i] = v;
+    if (xfull) *reinterpret_cast<double2*>(xfull + xfull_index(2 * i, cl, world, rank)) = v;
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    double v = w[n - 1] / beta;
-    q_next[n - 1] = v;
-    if (q_copy) q_copy[n - 1] = v;
+}
+
+// dir 0: xfull[slot(l)] = local[l]   dir 1: local[l] = xfull[slot(l)]
+__global__ void __launch_bounds__(kBlock) k_spread_collect(double* __restrict__ local, double* __restrict__ xfull, uint64_t n, uint64_t cl,
+                                                           uint32_t world, uint32_t rank, int dir) {
+  const uint64_t n2 = n >> 1;
+  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
+    double2* a = reinterpret_cast<double2*>(local) + i;
+    double2* b = reinterpret_cast<double2*>(xfull + xfull_index(2 * i, cl, world, rank));
+    if (dir == 0) *b = *a; else *a = *b;
   }
 }
 
@@ -496,8 +509,10 @@ __global__ void __launch_bounds__(kBlock) k_combine(const double* __restrict__ V
 constexpr int kEigMax = 1024;
 __global__ void __launch_bounds__(kBlock) k_tridiag_expv(uint32_t k, const double* __restrict__ alpha, const double* __restrict__ beta,
                                                          const double* __restrict__ xnorm2_p, double* __restrict__ eigvals,
-                                                         double* __restrict__ eigvecs, double* __restrict__ zt, double* __restrict__ coef,
-                                                         int* __restrict__ status) {
+                                                         double* __restrict__ eigvecs, double* __restrict__ zt_global, double* __restrict__ coef,
+                                                         int* __restrict__ status, int zt_in_smem) {
+  extern __shared__ double zt_smem[];
+  double* zt = zt_in_smem ? zt_smem : zt_global;   // k*k doubles: shared memory when it fits (k <= ~150), else global scratch
   __shared__ double d[kEigMax], e[kEigMax], cs[kEigMax], sn[kEigMax];
   __shared__ int perm[kEigMax];
   __shared__ int s_m, s_sweep, s_cont, s_fail;
@@ -529,7 +544,7 @@ __global__ void __launch_bounds__(kBlock) k_tridiag_expv(uint32_t k, const doubl
           else {
             double g = d[l];
             double p = (d[l + 1] - g) / (2.0 * e[l]);
-            double r = hypot(p, 1.0);
+            double r = sqrt(fma(p, p, 1.0));
             if (p < 0) r = -r;
             d[l] = e[l] / (p + r);
             d[l + 1] = e[l] * (p + r);
@@ -540,17 +555,23 @@ __global__ void __launch_bounds__(kBlock) k_tridiag_expv(uint32_t k, const doubl
             p = d[m];
             double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0;
             const double el1 = e[l + 1];
-            for (int i = m - 1; i >= l; i--) {
+            double ei = e[m - 1], di = d[m - 1];       // operands of the next rotation are fetched one rotation ahead so
+            for (int i = m - 1; i >= l; i--) {          // the shared-memory latency stays off the serial dependency chain
+              const double ei_next = (i > l) ? e[i - 1] : 0.0, di_next = (i > l) ? d[i - 1] : 0.0;
               c3 = c2; c2 = c; s2 = s;
-              g = c * e[i];
+              g = c * ei;
               h = c * p;
-              r = hypot(p, e[i]);
+              // |p|, |e_i| are bounded by ||T|| (graph spectra: << 1e150), so the unscaled form cannot overflow
+              const double rr = fma(p, p, ei * ei);
+              const double rinv = (rr > 0.0) ? rsqrt(rr) : 0.0;
+              r = rr * rinv;
               e[i + 1] = s * r;
-              s = e[i] / r;
-              c = p / r;
-              p = c * d[i] - s * g;
-              d[i + 1] = h + s * (c * g + s * d[i]);
+              s = ei * rinv;
+              c = (rr > 0.0) ? p * rinv : 1.0;
+              p = c * di - s * g;
+              d[i + 1] = h + s * (c * g + s * di);
               cs[i] = c; sn[i] = s;
+              ei = ei_next; di = di_next;
             }
             p = -s * s2 * c3 * el1 * e[l] / dl1;
             e[l] = s * p;
@@ -561,12 +582,14 @@ __global__ void __launch_bounds__(kBlock) k_tridiag_expv(uint32_t k, const doubl
         __syncthreads();
         if (s_sweep) {
           for (int q = tid; q < n; q += kBlock) {
+            double h = zt[m * n + q];                 // carried in a register from one rotation to the next
             for (int i = m - 1; i >= l; i--) {
               const double c = cs[i], s = sn[i];
-              const double h = zt[(i + 1) * n + q], z = zt[i * n + q];
+              const double z = zt[i * n + q];
               zt[(i + 1) * n + q] = s * z + c * h;
-              zt[i * n + q] = c * z - s * h;
+              h = c * z - s * h;
             }
+            zt[l * n + q] = h;
           }
         }
         const int cont = s_cont;
@@ -644,6 +667,8 @@ static int ensure_partials(lz_ctx* c, uint64_t count) {
 int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out) {
   for (uint32_t blk = 0; blk < c->ncolblk; blk++) {
     const int acc = blk > 0, fin = blk + 1 == c->ncolblk;
+    // pass `blk` gathers from chunk `blk` of the gathered vector only: wait for exactly that piece of the all-gather
+    if (c->chunks_in_flight) LZ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_chunk[blk], 0));
     if (c->spmv_variant == LZ_SPMV_AUTO) {          // sliced layout: long rows warp-per-row, short rows 32 per warp
       uint32_t grid = (uint32_t)c->sm_count * c->spmv_ctas_per_sm;
       const uint32_t need = (c->n_items + kWarps - 1) / kWarps;
@@ -663,6 +688,7 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
     }
     LZ_LAUNCH_CHECK();
   }
+  c->chunks_in_flight = false;
   return LZ_OK;
 }
 
@@ -675,9 +701,25 @@ int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev
   return LZ_OK;
 }
 
-int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* q_next_copy, double* beta_out) {
+int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* xfull, double* beta_out) {
   unsigned g = stream_grid(c, c->n_loc / 2 + 1);
-  k_scale<<<g, kBlock, 0, c->stream>>>(w, norm2, c->n_loc, q_next, q_next_copy, beta_out);
+  k_scale<<<g, kBlock, 0, c->stream>>>(w, norm2, c->n_loc, q_next, xfull, c->chunk_rows, (uint32_t)c->world, (uint32_t)c->rank, beta_out);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_spread(lz_ctx* c, const double* local, double* xfull) {
+  unsigned g = stream_grid(c, c->n_loc / 2 + 1);
+  k_spread_collect<<<g, kBlock, 0, c->stream>>>(const_cast<double*>(local), xfull, c->n_loc, c->chunk_rows, (uint32_t)c->world,
+                                                (uint32_t)c->rank, 0);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_collect(lz_ctx* c, const double* xfull, double* local) {
+  unsigned g = stream_grid(c, c->n_loc / 2 + 1);
+  k_spread_collect<<<g, kBlock, 0, c->stream>>>(local, const_cast<double*>(xfull), c->n_loc, c->chunk_rows, (uint32_t)c->world,
+                                                (uint32_t)c->rank, 1);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
@@ -712,7 +754,11 @@ int lz_k_combine(lz_ctx* c, const double* V, uint32_t nvec, const double* coef, 
 
 int lz_k_tridiag_expv(lz_ctx* c, uint32_t k) {
   if (k > (uint32_t)kEigMax) return lz_fail(LZ_ERR_ARG, "krylov dimension %u exceeds the on-device eigensolver limit %d", k, kEigMax);
-  k_tridiag_expv<<<1, kBlock, 0, c->stream>>>(k, c->alpha, c->beta, c->scal + 2, c->eigvals, c->eigvecs, c->eigwork, c->coef, c->status);
+  const size_t zt_bytes = (size_t)k * k * sizeof(double);
+  const int in_smem = zt_bytes <= 180 * 1024;
+  if (in_smem) LZ_CUDA(cudaFuncSetAttribute(k_tridiag_expv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zt_bytes));
+  k_tridiag_expv<<<1, kBlock, in_smem ? zt_bytes : 0, c->stream>>>(k, c->alpha, c->beta, c->scal + 2, c->eigvals, c->eigvecs, c->eigwork,
+                                                                  c->coef, c->status, in_smem);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
