@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 const lz_nccl_api* lz_nccl() {
   static lz_nccl_api api;
@@ -45,7 +46,21 @@ int set_dev(lz_ctx* c) {
   return LZ_OK;
 }
 
+void close_peers(lz_ctx* c) {
+  for (int r = 0; r < LZ_MAX_WORLD; r++) {
+    if (c->peer_ipc[r]) {
+      if (c->peer_xfull[r]) cudaIpcCloseMemHandle(c->peer_xfull[r]);
+      if (c->peer_flags[r]) cudaIpcCloseMemHandle(c->peer_flags[r]);
+    }
+    c->peer_xfull[r] = nullptr; c->peer_flags[r] = nullptr; c->peer_ipc[r] = false;
+  }
+  c->peer_push = false;
+}
+
 void free_vectors(lz_ctx* c) {
+  close_peers(c);
+  cudaFree(c->flags); cudaFree(c->push_ticket); cudaFree(c->gfull);
+  c->flags = nullptr; c->push_ticket = nullptr; c->gfull = nullptr;
   cudaFree(c->V); cudaFree(c->w); cudaFree(c->xfull); cudaFree(c->xstage); cudaFree(c->ans);
   cudaFree(c->alpha); cudaFree(c->beta); cudaFree(c->hcoef); cudaFree(c->eigvals); cudaFree(c->eigvecs); cudaFree(c->eigwork);
   cudaFree(c->coef);
@@ -54,11 +69,87 @@ void free_vectors(lz_ctx* c) {
   c->have_x = c->have_tridiag = c->have_coef = c->have_ans = false;
 }
 
+// Peer exchange set-up (collective: every rank calls it at the same point). Each rank publishes CUDA IPC handles of its
+// gathered vector and arrival counters; ranks living in the same process (one host thread per GPU) use the raw pointers
+// with peer access enabled instead. The decision to use the peer path is agreed by an all-reduce so no rank diverges.
+struct lz_xchg {
+  cudaIpcMemHandle_t hx, hf;
+  unsigned long long pid, px, pf;
+  int device, ok;
+};
+
+int setup_peers(lz_ctx* c) {
+  c->peer_push = false;
+  if (c->world == 1) return LZ_OK;
+  bool want = c->world <= LZ_MAX_WORLD;
+  if (const char* e = getenv("LZ_PEER_PUSH")) want = want && atoi(e) != 0;
+  LZ_CUDA(cudaMalloc((void**)&c->flags, sizeof(unsigned long long) * LZ_MAX_COLBLK * LZ_MAX_WORLD));
+  LZ_CUDA(cudaMemsetAsync(c->flags, 0, sizeof(unsigned long long) * LZ_MAX_COLBLK * LZ_MAX_WORLD, c->stream));
+  LZ_CUDA(cudaMalloc((void**)&c->push_ticket, sizeof(unsigned int) * LZ_MAX_COLBLK));
+  LZ_CUDA(cudaMemsetAsync(c->push_ticket, 0, sizeof(unsigned int) * LZ_MAX_COLBLK, c->stream));
+  c->push_seq = 0;
+  const int W = c->world;
+  std::vector<lz_xchg> all(W);
+  lz_xchg mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.pid = (unsigned long long)getpid(); mine.px = (unsigned long long)c->xfull; mine.pf = (unsigned long long)c->flags;
+  mine.device = c->device;
+  mine.ok = want && cudaIpcGetMemHandle(&mine.hx, c->xfull) == cudaSuccess && cudaIpcGetMemHandle(&mine.hf, c->flags) == cudaSuccess;
+  cudaGetLastError();
+  lz_xchg* dbuf = nullptr;
+  LZ_CUDA(cudaMalloc((void**)&dbuf, sizeof(lz_xchg) * W));
+  LZ_CUDA(cudaMemcpyAsync(dbuf + c->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+  LZ_NCCL(lz_nccl()->AllGather(dbuf + c->rank, dbuf, sizeof(lz_xchg), ncclChar, c->comm, c->stream));
+  LZ_CUDA(cudaMemcpyAsync(all.data(), dbuf, sizeof(lz_xchg) * W, cudaMemcpyDeviceToHost, c->stream));
+  LZ_CUDA(cudaStreamSynchronize(c->stream));
+  int ok = 1;
+  for (int r = 0; r < W; r++) ok &= all[r].ok;
+  for (int r = 0; r < W && ok; r++) {
+    if (r == c->rank) { c->peer_xfull[r] = c->xfull; c->peer_flags[r] = c->flags; continue; }
+    if (all[r].pid == mine.pid) {                       // same process, another host thread: raw pointers + peer access
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, c->device, all[r].device) != cudaSuccess || !can) { ok = 0; break; }
+      cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = 0; break; }
+      cudaGetLastError();
+      c->peer_xfull[r] = (double*)all[r].px; c->peer_flags[r] = (unsigned long long*)all[r].pf;
+    } else {
+      void *px = nullptr, *pf = nullptr;
+      if (cudaIpcOpenMemHandle(&px, all[r].hx, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&pf, all[r].hf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        if (px) cudaIpcCloseMemHandle(px);
+        ok = 0;
+        break;
+      }
+      c->peer_xfull[r] = (double*)px; c->peer_flags[r] = (unsigned long long*)pf; c->peer_ipc[r] = true;
+    }
+  }
+  // agree: the peer path is used only if every rank mapped every peer
+  double* flag_d = c->scal + 8;
+  double okd = ok ? 1.0 : 0.0;
+  LZ_CUDA(cudaMemcpyAsync(flag_d, &okd, 8, cudaMemcpyHostToDevice, c->stream));
+  LZ_NCCL(lz_nccl()->AllReduce(flag_d, flag_d, 1, ncclDouble, ncclMin, c->comm, c->stream));
+  LZ_CUDA(cudaMemcpyAsync(&okd, flag_d, 8, cudaMemcpyDeviceToHost, c->stream));
+  LZ_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(dbuf);
+  if (okd < 0.5) { close_peers(c); return LZ_OK; }
+  c->peer_push = true;
+  return LZ_OK;
+}
+
 // Vectors that depend only on the graph size.
 int ensure_graph_vectors(lz_ctx* c) {
   if (!c->row_ptr) return lz_fail(LZ_ERR_ARG, "no graph loaded (call lz_csr_upload or lz_graph_generate first)");
   const uint64_t ldv = (c->n_loc + 31) & ~31ull;
   if (c->w && c->ldv == ldv && c->vec_n == c->n && c->vec_nloc == c->n_loc) return LZ_OK;
+  if (c->world > 1 && c->xfull) {
+    // peers may still map this rank's buffers: everybody unmaps first, then (after a barrier) everybody frees
+    close_peers(c);
+    double* b = c->scal + 9;
+    LZ_NCCL(lz_nccl()->AllReduce(b, b, 1, ncclDouble, ncclSum, c->comm, c->stream));
+    LZ_CUDA(cudaStreamSynchronize(c->stream));
+  }
   free_vectors(c);
   c->ldv = ldv; c->vec_n = c->n; c->vec_nloc = c->n_loc;
   LZ_CUDA(cudaMalloc((void**)&c->w, ldv * 8));
@@ -67,6 +158,9 @@ int ensure_graph_vectors(lz_ctx* c) {
   LZ_CUDA(cudaMalloc((void**)&c->xfull, c->n_loc * (uint64_t)c->world * 8));
   LZ_CUDA(cudaMemsetAsync(c->w, 0, ldv * 8, c->stream));
   LZ_CUDA(cudaMemsetAsync(c->ans, 0, ldv * 8, c->stream));
+  LZ_CUDA(cudaMemsetAsync(c->xfull, 0, c->n_loc * (uint64_t)c->world * 8, c->stream));
+  if (c->world > 1) LZ_CUDA(cudaMalloc((void**)&c->gfull, c->n_loc * (uint64_t)c->world * 8));
+  LZ_TRY(setup_peers(c));
   return LZ_OK;
 }
 
@@ -270,8 +364,7 @@ extern "C" int lz_set_start_vector(lz_ctx* c, const double* x_host) {
   }
   LZ_TRY(lz_k_norm2(c, c->xstage, c->n, c->scal + 2));
   if (c->world > 1) {
-    LZ_TRY(lz_k_permute_in(c, c->xstage, c->scal + 2, 0, c->n_loc * (uint64_t)c->world, c->xfull));   // every rank has all of x
-    LZ_TRY(lz_k_collect(c, c->xfull, c->V));
+    LZ_TRY(lz_k_permute_in_local(c, c->xstage, c->scal + 2, c->V));   // own rows only; the gathered vector is filled by the run
   } else {
     LZ_TRY(lz_k_permute_in(c, c->xstage, c->scal + 2, 0, c->n_loc, c->V));
   }
@@ -293,14 +386,18 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
   g_marks.clear();
   LZ_CUDA(cudaEventRecord(c->ev_a, c->stream));
   if (dist) {   // q_0 into the gathered buffer (a previous run left q_{k-1} there)
-    LZ_TRY(lz_k_spread(c, c->V, c->xfull));
-    LZ_TRY(allgather_chunks(c, c->xfull, true));
+    if (c->peer_push) {
+      LZ_TRY(lz_k_scale_push(c, c->V, nullptr, c->V, nullptr, ++c->push_seq));
+    } else {
+      LZ_TRY(lz_k_spread(c, c->V, c->xfull));
+      LZ_TRY(allgather_chunks(c, c->xfull, true));
+    }
   }
   for (uint32_t j = 0; j < k; j++) {
     double* qj = c->V + (uint64_t)j * ldv;
     {  // w = A q_j ; alpha_j = w . q_j                                   (cu_lanczos.cu:101-105)
       Scope s(c, 0);
-      LZ_TRY(lz_k_spmv_dot(c, dist ? c->xfull : qj, qj, c->w, c->alpha + j));
+      LZ_TRY(lz_k_spmv_dot(c, dist ? c->xfull : qj, qj, c->w, c->alpha + j, c->peer_push ? c->push_seq : 0ull));
     }
     LZ_TRY(allreduce_sum(c, c->alpha + j, 1));
     if (j + 1 == k) break;                                               // last step needs alpha only (cu_lanczos.cu:116)
@@ -320,9 +417,10 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
     LZ_TRY(allreduce_sum(c, c->scal + 1, 1));
     {  // beta_j = ||w|| ; q_{j+1} = w / beta_j                            (cu_lanczos.cu:120-123)
       Scope s(c, 1);
-      LZ_TRY(lz_k_scale(c, c->w, c->scal + 1, qj + ldv, dist ? c->xfull : nullptr, c->beta + j));
+      if (c->peer_push) LZ_TRY(lz_k_scale_push(c, c->w, c->scal + 1, qj + ldv, c->beta + j, ++c->push_seq));
+      else LZ_TRY(lz_k_scale(c, c->w, c->scal + 1, qj + ldv, dist ? c->xfull : nullptr, c->beta + j));
     }
-    LZ_TRY(allgather_chunks(c, c->xfull, true));
+    if (!c->peer_push) LZ_TRY(allgather_chunks(c, c->xfull, true));
   }
   LZ_CUDA(cudaEventRecord(c->ev_b, c->stream));
   c->k_done = k;
@@ -389,9 +487,9 @@ static int gather_to_host(lz_ctx* c, const double* local, double* host_out) {
   // local [n_loc] (new order, this rank's slice) -> host [n] original order, on every rank
   const double* full = local;
   if (c->world > 1) {
-    LZ_TRY(lz_k_spread(c, local, c->xfull));
-    LZ_TRY(allgather_chunks(c, c->xfull, false));
-    full = c->xfull;
+    LZ_TRY(lz_k_spread(c, local, c->gfull));   // not xfull: a faster peer may already be pushing the next run's q_0 there
+    LZ_TRY(allgather_chunks(c, c->gfull, false));
+    full = c->gfull;
   }
   LZ_TRY(lz_k_permute_out(c, full, c->xstage));
   LZ_CUDA(cudaMemcpyAsync(host_out, c->xstage, c->n * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -42,6 +42,7 @@ const lz_nccl_api* lz_nccl();   // nullptr (with lz_last_error set) when no libn
 // kernel variant (lanes-per-row = 1 << log2_lanes) serves.
 #define LZ_MAX_BINS 8
 #define LZ_MAX_COLBLK 32
+#define LZ_MAX_WORLD 16
 #define LZ_SELL_LONG 128          // rows longer than this are served warp-per-row
 #define LZ_SPMV_BLOCK 256         // threads per CTA of the SpMV kernel
 #define LZ_SPMV_ROWS_PER_GROUP 4  // rows handled concurrently by one lane group (memory-level parallelism)
@@ -65,7 +66,17 @@ struct lz_ctx {
   cudaStream_t stream = nullptr, comm_stream = nullptr;
   cudaEvent_t ev_scaled = nullptr, ev_chunk[LZ_MAX_COLBLK] = {};
   bool comm_overlap = true;
-  bool chunks_in_flight = false;   // ev_chunk[] were recorded for the vector the next SpMV gathers from
+  bool chunks_in_flight = false;
+  // Peer exchange (default for world > 1): k_scale stores q_{j+1} straight into every rank's gathered vector over NVLink
+  // and raises per-chunk arrival counters there; SpMV pass b spins on chunk b's counters. No collective, no extra pass.
+  bool peer_push = false;
+  double* peer_xfull[LZ_MAX_WORLD] = {};              // every rank's xfull as seen from this GPU (own included)
+  unsigned long long* peer_flags[LZ_MAX_WORLD] = {};  // every rank's arrival counters
+  bool peer_ipc[LZ_MAX_WORLD] = {};                   // mapping came from cudaIpcOpenMemHandle (must be closed)
+  unsigned long long* flags = nullptr;                // device, [LZ_MAX_COLBLK][LZ_MAX_WORLD], written by the peers
+  unsigned int* push_ticket = nullptr;                // device, [LZ_MAX_COLBLK]
+  unsigned long long push_seq = 0;                    // sequence number of the last push (same on every rank)
+  double* gfull = nullptr;                            // device, [n_loc * world], scratch for the host-facing gathers   // ev_chunk[] were recorded for the vector the next SpMV gathers from
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;      // lz_lanczos_run
   cudaEvent_t ev_e0 = nullptr, ev_e1 = nullptr;    // lz_tridiag_expv
   cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;    // lz_multout
@@ -143,11 +154,16 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
 void lz_free_graph(lz_ctx* c);
 
 // lz_kernels.cu — all launches are asynchronous on c->stream
-int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out /* device scalar or null */);
+int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out /* device scalar or null */,
+                  unsigned long long wait_seq = 0 /* > 0: pass b first waits until chunk b of x_gather has arrived from every rank */);
 int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev, const double* alpha, const double* beta_prev,
                      double* norm2_out /* device scalar or null */);
 // q_next = w / sqrt(*norm2); when xfull != null also stores it into this rank's slots of the chunk-major gathered vector
 int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* xfull, double* beta_out);
+// peer exchange: q_next = w / sqrt(*norm2) (norm2 == null: plain copy of w) stored locally and into every rank's gathered vector; raises seq
+int lz_k_scale_push(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* beta_out, unsigned long long seq);
+// q0_local[l] = x_orig[new2old[slot(l)]] / sqrt(*norm2)
+int lz_k_permute_in_local(lz_ctx* c, const double* x_orig, const double* norm2, double* q0_local);
 // local vector <-> this rank's slots of the chunk-major gathered vector
 int lz_k_spread(lz_ctx* c, const double* local, double* xfull);
 int lz_k_collect(lz_ctx* c, const double* xfull, double* local);

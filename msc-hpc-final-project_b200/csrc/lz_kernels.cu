@@ -70,6 +70,32 @@ __device__ __forceinline__ void grid_sum_finish(double cta_val, double* partials
   }
 }
 
+// ---- peer exchange over NVLink ---------------------------------------------------------------------------------------
+struct lz_peers {
+  double* x[LZ_MAX_WORLD];
+  unsigned long long* f[LZ_MAX_WORLD];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Consumer side: block until chunk `blk` of the gathered vector has been written by every rank (counter >= seq).
+// The producers are kernels on OTHER GPUs that never wait for this GPU's SpMV, so this cannot deadlock.
+__device__ __forceinline__ void wait_chunk(const unsigned long long* flags, uint32_t blk, uint32_t world, unsigned long long seq) {
+  if (seq == 0) return;
+  if (threadIdx.x < world) {
+    const unsigned long long* f = flags + (uint64_t)blk * LZ_MAX_WORLD + threadIdx.x;
+    while (ld_acquire_sys(f) < seq) __nanosleep(64);
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------------------- SpMV
 // Value-less CSR gather-sum. One row is served by L = 2^LG cooperating lanes ("vector per row"; L = 32 is warp per row).
 // Local rows are sorted by length, so every row of a bin has len in (L, 2L] (L = 1: len <= 2; L = 32: len > 32): all
@@ -172,9 +198,11 @@ __global__ void __launch_bounds__(kBlock) k_spmv_dot(const __grid_constant__ lz_
                                                      const uint32_t* __restrict__ seg_hi, const uint32_t* __restrict__ col,
                                                      const double* __restrict__ x, const double* __restrict__ q, double* __restrict__ w,
                                                      double* partials, unsigned int* ticket, double* alpha_out, int accumulate,
-                                                     int final_pass) {
+                                                     int final_pass, const unsigned long long* flags, uint32_t blk, uint32_t world,
+                                                     unsigned long long wait_seq) {
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
+  wait_chunk(flags, blk, world, wait_seq);
   double d = 0.0;
   const bool acc = accumulate != 0, fin = final_pass != 0;
   for (uint32_t item = blockIdx.x; item < plan.nitems; item += gridDim.x) {
@@ -213,9 +241,12 @@ constexpr int kSellU = 8;   // chunks (gathers per lane) in flight
 __global__ void __launch_bounds__(kBlock) k_spmv_sell(const uint32_t* __restrict__ sp, const uint32_t* __restrict__ scol, uint32_t n_long,
                                                       uint32_t n_items, uint32_t n_loc, const double* __restrict__ x,
                                                       const double* __restrict__ q, double* __restrict__ w, double* partials,
-                                                      unsigned int* ticket, double* alpha_out, int accumulate, int final_pass) {
+                                                      unsigned int* ticket, double* alpha_out, int accumulate, int final_pass,
+                                                      const unsigned long long* flags, uint32_t blk, uint32_t world,
+                                                      unsigned long long wait_seq) {
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
+  wait_chunk(flags, blk, world, wait_seq);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t nwarps = gridDim.x * kWarps;
   double d = 0.0;
@@ -333,6 +364,54 @@ __global__ void __launch_bounds__(kBlock) k_scale(const double* __restrict__ w, 
     v.y /= beta;
     q2[i] = v;
     if (xfull) *reinterpret_cast<double2*>(xfull + xfull_index(2 * i, cl, world, rank)) = v;
+  }
+}
+
+// Producer side of the peer exchange, fused into the normalisation: q_next = w / beta is stored locally and, 16 bytes at a
+// time, into the chunk-major gathered vector of EVERY rank (peer stores over NVLink; own rank included). Rows are
+// processed chunk by chunk; when the last CTA has finished a chunk it publishes `seq` in every rank's arrival counter for
+// (chunk, this rank), so remote SpMV passes over early (hot) chunks start while later chunks are still being sent.
+__global__ void __launch_bounds__(kBlock) k_scale_push(const double* __restrict__ w, const double* __restrict__ norm2_p, uint64_t n,
+                                                       double* __restrict__ q_next, const __grid_constant__ lz_peers peers, uint64_t cl,
+                                                       uint32_t nchunks, uint32_t world, uint32_t rank, unsigned long long seq,
+                                                       unsigned int* ticket, double* beta_out) {
+  const double beta = norm2_p ? sqrt(*norm2_p) : 1.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && beta_out) *beta_out = beta;
+  const double2* w2 = reinterpret_cast<const double2*>(w);
+  double2* q2 = reinterpret_cast<double2*>(q_next);
+  const uint64_t cl2 = cl >> 1;
+  __shared__ bool s_last;
+  for (uint32_t c = 0; c < nchunks; c++) {
+    const uint64_t slot2 = ((uint64_t)c * world * cl + (uint64_t)rank * cl) >> 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < cl2; i += (uint64_t)gridDim.x * kBlock) {
+      const uint64_t li = (uint64_t)c * cl2 + i;
+      double2 v = w2[li];
+      if (norm2_p) { v.x /= beta; v.y /= beta; }
+      if (q_next != w) q2[li] = v;
+      for (uint32_t r = 0; r < world; r++) reinterpret_cast<double2*>(peers.x[r])[slot2 + i] = v;
+    }
+    __threadfence_system();          // this thread's peer stores are visible system-wide before the CTA reports in
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int t = atomicAdd(ticket + c, 1u);
+      s_last = (t == gridDim.x - 1);
+      if (s_last) {
+        ticket[c] = 0u;
+        __threadfence_system();
+        for (uint32_t r = 0; r < world; r++) st_release_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, seq);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// q0_local[l] = x_orig[new2old[slot(l)]] / sqrt(norm2)
+__global__ void k_permute_in_local(const double* __restrict__ x_orig, const uint32_t* __restrict__ new2old, uint64_t n, uint64_t cl,
+                                   uint32_t world, uint32_t rank, const double* __restrict__ norm2_p, double* __restrict__ dst) {
+  const double nrm = sqrt(*norm2_p);
+  for (uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t o = new2old[xfull_index(l, cl, world, rank)];
+    dst[l] = (o == 0xFFFFFFFFu) ? 0.0 : x_orig[o] / nrm;
   }
 }
 
@@ -664,7 +743,7 @@ static int ensure_partials(lz_ctx* c, uint64_t count) {
   return LZ_OK;
 }
 
-int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out) {
+int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out, unsigned long long wait_seq) {
   for (uint32_t blk = 0; blk < c->ncolblk; blk++) {
     const int acc = blk > 0, fin = blk + 1 == c->ncolblk;
     // pass `blk` gathers from chunk `blk` of the gathered vector only: wait for exactly that piece of the all-gather
@@ -676,7 +755,8 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
       if (grid < 1) grid = 1;
       LZ_TRY(ensure_partials(c, grid));
       k_spmv_sell<<<grid, kBlock, 0, c->stream>>>(c->sell_sp + (uint64_t)blk * c->n_items, c->sell_col, c->n_long, c->n_items,
-                                                  (uint32_t)c->n_loc, x_gather, q_local, w_out, c->partials, c->ticket + 0, alpha_out, acc, fin);
+                                                  (uint32_t)c->n_loc, x_gather, q_local, w_out, c->partials, c->ticket + 0, alpha_out, acc, fin,
+                                                  c->flags, blk, (uint32_t)c->world, wait_seq);
     } else {                                         // CSR: vector (sub-warp) per row by degree bin, or warp per row
       const lz_spmv_plan& plan = (c->spmv_variant == LZ_SPMV_WARP) ? c->plan_warp : c->plan_auto[blk];
       if (plan.nitems == 0) return lz_fail(LZ_ERR_ARG, "empty SpMV plan");
@@ -684,7 +764,7 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
       if (grid > plan.nitems) grid = plan.nitems;
       LZ_TRY(ensure_partials(c, grid));
       k_spmv_dot<<<grid, kBlock, 0, c->stream>>>(plan, c->seg[blk], c->seg[blk] + 1, c->col, x_gather, q_local, w_out, c->partials,
-                                                 c->ticket + 0, alpha_out, acc, fin);
+                                                 c->ticket + 0, alpha_out, acc, fin, c->flags, blk, (uint32_t)c->world, wait_seq);
     }
     LZ_LAUNCH_CHECK();
   }
@@ -704,6 +784,26 @@ int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev
 int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* xfull, double* beta_out) {
   unsigned g = stream_grid(c, c->n_loc / 2 + 1);
   k_scale<<<g, kBlock, 0, c->stream>>>(w, norm2, c->n_loc, q_next, xfull, c->chunk_rows, (uint32_t)c->world, (uint32_t)c->rank, beta_out);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_scale_push(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* beta_out, unsigned long long seq) {
+  lz_peers peers;
+  for (int r = 0; r < LZ_MAX_WORLD; r++) { peers.x[r] = c->peer_xfull[r]; peers.f[r] = c->peer_flags[r]; }
+  // few CTAs suffice to saturate NVLink; cap so the per-chunk ticketing stays cheap
+  unsigned g = stream_grid(c, c->chunk_rows / 2 + 1);
+  const unsigned cap = (unsigned)c->sm_count * 2;
+  if (g > cap) g = cap;
+  k_scale_push<<<g, kBlock, 0, c->stream>>>(w, norm2, c->n_loc, q_next, peers, c->chunk_rows, c->ncolblk, (uint32_t)c->world,
+                                            (uint32_t)c->rank, seq, c->push_ticket, beta_out);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_permute_in_local(lz_ctx* c, const double* x_orig, const double* norm2, double* q0_local) {
+  k_permute_in_local<<<stream_grid(c, c->n_loc), kBlock, 0, c->stream>>>(x_orig, c->new2old, c->n_loc, c->chunk_rows, (uint32_t)c->world,
+                                                                        (uint32_t)c->rank, norm2, q0_local);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
