@@ -382,12 +382,15 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
   LZ_TRY(ensure_k(c, k));
   const uint64_t ldv = c->ldv;
   const bool dist = c->world > 1;
+  // chunk 0 of each new vector is sent by the normalisation kernel, chunk b + 1 by SpMV pass b (sliced variant only)
+  bool fused_push = c->peer_push && c->spmv_variant == LZ_SPMV_AUTO && c->ncolblk > 1;
+  if (const char* e = getenv("LZ_FUSED_PUSH")) fused_push = fused_push && atoi(e) != 0;
   c->ev_used = 0;
   g_marks.clear();
   LZ_CUDA(cudaEventRecord(c->ev_a, c->stream));
   if (dist) {   // q_0 into the gathered buffer (a previous run left q_{k-1} there)
     if (c->peer_push) {
-      LZ_TRY(lz_k_scale_push(c, c->V, nullptr, c->V, nullptr, ++c->push_seq));
+      LZ_TRY(lz_k_scale_push(c, c->V, nullptr, c->V, nullptr, ++c->push_seq, fused_push ? 1u : c->ncolblk));
     } else {
       LZ_TRY(lz_k_spread(c, c->V, c->xfull));
       LZ_TRY(allgather_chunks(c, c->xfull, true));
@@ -397,7 +400,7 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
     double* qj = c->V + (uint64_t)j * ldv;
     {  // w = A q_j ; alpha_j = w . q_j                                   (cu_lanczos.cu:101-105)
       Scope s(c, 0);
-      LZ_TRY(lz_k_spmv_dot(c, dist ? c->xfull : qj, qj, c->w, c->alpha + j, c->peer_push ? c->push_seq : 0ull));
+      LZ_TRY(lz_k_spmv_dot(c, dist ? c->xfull : qj, qj, c->w, c->alpha + j, c->peer_push ? c->push_seq : 0ull, fused_push ? qj : nullptr));
     }
     LZ_TRY(allreduce_sum(c, c->alpha + j, 1));
     if (j + 1 == k) break;                                               // last step needs alpha only (cu_lanczos.cu:116)
@@ -417,7 +420,7 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
     LZ_TRY(allreduce_sum(c, c->scal + 1, 1));
     {  // beta_j = ||w|| ; q_{j+1} = w / beta_j                            (cu_lanczos.cu:120-123)
       Scope s(c, 1);
-      if (c->peer_push) LZ_TRY(lz_k_scale_push(c, c->w, c->scal + 1, qj + ldv, c->beta + j, ++c->push_seq));
+      if (c->peer_push) LZ_TRY(lz_k_scale_push(c, c->w, c->scal + 1, qj + ldv, c->beta + j, ++c->push_seq, fused_push ? 1u : c->ncolblk));
       else LZ_TRY(lz_k_scale(c, c->w, c->scal + 1, qj + ldv, dist ? c->xfull : nullptr, c->beta + j));
     }
     if (!c->peer_push) LZ_TRY(allgather_chunks(c, c->xfull, true));

@@ -155,13 +155,15 @@ void lz_free_graph(lz_ctx* c);
 
 // lz_kernels.cu — all launches are asynchronous on c->stream
 int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out /* device scalar or null */,
-                  unsigned long long wait_seq = 0 /* > 0: pass b first waits until chunk b of x_gather has arrived from every rank */);
+                  unsigned long long wait_seq = 0 /* > 0: pass b first waits until chunk b of x_gather has arrived from every rank */,
+                  const double* push_src = nullptr /* sliced variant only: pass b also sends chunk b + 1 of this local vector */);
 int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev, const double* alpha, const double* beta_prev,
                      double* norm2_out /* device scalar or null */);
 // q_next = w / sqrt(*norm2); when xfull != null also stores it into this rank's slots of the chunk-major gathered vector
 int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* xfull, double* beta_out);
 // peer exchange: q_next = w / sqrt(*norm2) (norm2 == null: plain copy of w) stored locally and into every rank's gathered vector; raises seq
-int lz_k_scale_push(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* beta_out, unsigned long long seq);
+int lz_k_scale_push(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* beta_out, unsigned long long seq,
+                    uint32_t push_chunks /* chunks [0, push_chunks) are sent here; the rest by the SpMV passes */);
 // q0_local[l] = x_orig[new2old[slot(l)]] / sqrt(*norm2)
 int lz_k_permute_in_local(lz_ctx* c, const double* x_orig, const double* norm2, double* q0_local);
 // local vector <-> this rank's slots of the chunk-major gathered vector

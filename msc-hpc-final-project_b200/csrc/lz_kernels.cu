@@ -50,18 +50,19 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 // Deterministic grid reduction tail. Thread 0 of every CTA passes its CTA value; the last CTA to arrive sums all
 // `gridDim.x` partials in index order (strided per thread, then a fixed tree) and stores op(sum) to *out.
 __device__ __forceinline__ void grid_sum_finish(double cta_val, double* partials, unsigned int* ticket, double* out, double* sm,
-                                                bool* s_last) {
+                                                bool* s_last, unsigned int cta = 0xFFFFFFFFu, unsigned int nctas = 0) {
+  if (cta == 0xFFFFFFFFu) { cta = blockIdx.x; nctas = gridDim.x; }   // default: every CTA of the grid takes part
   if (threadIdx.x == 0) {
-    partials[blockIdx.x] = cta_val;
+    partials[cta] = cta_val;
     __threadfence();
     unsigned int t = atomicAdd(ticket, 1u);
-    *s_last = (t == gridDim.x - 1);
+    *s_last = (t == nctas - 1);
   }
   __syncthreads();
   if (*s_last) {
     __threadfence();
     double acc = 0.0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) acc += __ldcg(partials + i);
+    for (unsigned int i = threadIdx.x; i < nctas; i += kBlock) acc += __ldcg(partials + i);
     acc = block_sum(acc, sm);
     if (threadIdx.x == 0) {
       *out = acc;
@@ -74,6 +75,15 @@ __device__ __forceinline__ void grid_sum_finish(double cta_val, double* partials
 struct lz_peers {
   double* x[LZ_MAX_WORLD];
   unsigned long long* f[LZ_MAX_WORLD];
+};
+
+struct lz_push_job {     // work of the sender CTAs fused into an SpMV pass (nctas == 0: none)
+  lz_peers peers;
+  const double* src;
+  unsigned int* ticket;
+  unsigned long long seq;
+  uint64_t cl;
+  uint32_t chunk, rank, nctas;
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -91,7 +101,44 @@ __device__ __forceinline__ void wait_chunk(const unsigned long long* flags, uint
   if (seq == 0) return;
   if (threadIdx.x < world) {
     const unsigned long long* f = flags + (uint64_t)blk * LZ_MAX_WORLD + threadIdx.x;
-    while (ld_acquire_sys(f) < seq) __nanosleep(64);
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    while (ld_acquire_sys(f) < seq) {
+      __nanosleep(64);
+      if ((++spins & 0xFFFFu) == 0) {                      // watchdog: a lost peer becomes a launch failure, not a hang
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) __trap();      // 20 s
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Producer side: copy chunk `c` of this rank's local vector `src` (already normalised) into the chunk-major gathered vector
+// of every rank (16-byte peer stores over NVLink), then — once all `nctas` participating CTAs are done — publish `seq` in
+// every rank's arrival counter for (chunk c, this rank). `cta` is this CTA's index among the participants.
+__device__ __forceinline__ void push_chunk(const double* __restrict__ src, const lz_peers& peers, uint32_t c, uint64_t cl, uint32_t world,
+                                           uint32_t rank, unsigned long long seq, unsigned int* ticket, uint32_t cta, uint32_t nctas,
+                                           bool* s_flag) {
+  const uint64_t cl2 = cl >> 1;
+  const uint64_t slot2 = ((uint64_t)c * world * cl + (uint64_t)rank * cl) >> 1;
+  const double2* s2 = reinterpret_cast<const double2*>(src) + (uint64_t)c * cl2;
+  for (uint64_t i = (uint64_t)cta * kBlock + threadIdx.x; i < cl2; i += (uint64_t)nctas * kBlock) {
+    const double2 v = s2[i];
+    for (uint32_t r = 0; r < world; r++) reinterpret_cast<double2*>(peers.x[r])[slot2 + i] = v;
+  }
+  __threadfence_system();          // this thread's peer stores are visible system-wide before the CTA reports in
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket + c, 1u);
+    *s_flag = (t == nctas - 1);
+    if (*s_flag) {
+      ticket[c] = 0u;
+      __threadfence_system();
+      for (uint32_t r = 0; r < world; r++) st_release_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, seq);
+    }
   }
   __syncthreads();
 }
@@ -243,14 +290,22 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell(const uint32_t* __restrict
                                                       const double* __restrict__ q, double* __restrict__ w, double* partials,
                                                       unsigned int* ticket, double* alpha_out, int accumulate, int final_pass,
                                                       const unsigned long long* flags, uint32_t blk, uint32_t world,
-                                                      unsigned long long wait_seq) {
+                                                      unsigned long long wait_seq, const __grid_constant__ lz_push_job job) {
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
+  // Fused exchange: the first job.nctas CTAs of pass `blk` send chunk job.chunk (= blk + 1) of the new Krylov vector to
+  // every rank while the remaining CTAs gather from chunk blk. Senders never wait, gatherers wait only for data sent by
+  // strictly earlier launches on every rank, so the scheme cannot deadlock whatever the CTA placement.
+  if (blockIdx.x < job.nctas) {
+    push_chunk(job.src, job.peers, job.chunk, job.cl, world, job.rank, job.seq, job.ticket, blockIdx.x, job.nctas, &s_last);
+    return;
+  }
+  const uint32_t cta = blockIdx.x - job.nctas, nctas = gridDim.x - job.nctas;
   wait_chunk(flags, blk, world, wait_seq);
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t nwarps = gridDim.x * kWarps;
+  const uint32_t nwarps = nctas * kWarps;
   double d = 0.0;
-  for (uint32_t item = blockIdx.x * kWarps + (threadIdx.x >> 5); item < n_items; item += nwarps) {
+  for (uint32_t item = cta * kWarps + (threadIdx.x >> 5); item < n_items; item += nwarps) {
     const uint32_t c0 = __ldg(sp + item), nchunk = __ldg(sp + item + 1) - c0;
     const uint32_t* p = scol + (uint64_t)c0 * 32 + lane;
     double acc = 0.0;
@@ -300,7 +355,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell(const uint32_t* __restrict
   }
   if (final_pass) {
     d = block_sum(d, sm);
-    grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last);
+    grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last, cta, nctas);
   }
 }
 
@@ -373,8 +428,8 @@ __global__ void __launch_bounds__(kBlock) k_scale(const double* __restrict__ w, 
 // (chunk, this rank), so remote SpMV passes over early (hot) chunks start while later chunks are still being sent.
 __global__ void __launch_bounds__(kBlock) k_scale_push(const double* __restrict__ w, const double* __restrict__ norm2_p, uint64_t n,
                                                        double* __restrict__ q_next, const __grid_constant__ lz_peers peers, uint64_t cl,
-                                                       uint32_t nchunks, uint32_t world, uint32_t rank, unsigned long long seq,
-                                                       unsigned int* ticket, double* beta_out) {
+                                                       uint32_t nchunks, uint32_t push_chunks, uint32_t world, uint32_t rank,
+                                                       unsigned long long seq, unsigned int* ticket, double* beta_out) {
   const double beta = norm2_p ? sqrt(*norm2_p) : 1.0;
   if (blockIdx.x == 0 && threadIdx.x == 0 && beta_out) *beta_out = beta;
   const double2* w2 = reinterpret_cast<const double2*>(w);
@@ -382,14 +437,17 @@ __global__ void __launch_bounds__(kBlock) k_scale_push(const double* __restrict_
   const uint64_t cl2 = cl >> 1;
   __shared__ bool s_last;
   for (uint32_t c = 0; c < nchunks; c++) {
+    const bool send = c < push_chunks;
     const uint64_t slot2 = ((uint64_t)c * world * cl + (uint64_t)rank * cl) >> 1;
     for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < cl2; i += (uint64_t)gridDim.x * kBlock) {
       const uint64_t li = (uint64_t)c * cl2 + i;
       double2 v = w2[li];
       if (norm2_p) { v.x /= beta; v.y /= beta; }
       if (q_next != w) q2[li] = v;
-      for (uint32_t r = 0; r < world; r++) reinterpret_cast<double2*>(peers.x[r])[slot2 + i] = v;
+      if (send)
+        for (uint32_t r = 0; r < world; r++) reinterpret_cast<double2*>(peers.x[r])[slot2 + i] = v;
     }
+    if (!send) continue;
     __threadfence_system();          // this thread's peer stores are visible system-wide before the CTA reports in
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -743,8 +801,16 @@ static int ensure_partials(lz_ctx* c, uint64_t count) {
   return LZ_OK;
 }
 
-int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out, unsigned long long wait_seq) {
+int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out, unsigned long long wait_seq,
+                  const double* push_src) {
   for (uint32_t blk = 0; blk < c->ncolblk; blk++) {
+    lz_push_job job;
+    memset(&job, 0, sizeof(job));
+    if (push_src && blk + 1 < c->ncolblk) {      // this pass also sends chunk blk + 1 of the vector being gathered
+      for (int r = 0; r < LZ_MAX_WORLD; r++) { job.peers.x[r] = c->peer_xfull[r]; job.peers.f[r] = c->peer_flags[r]; }
+      job.src = push_src; job.ticket = c->push_ticket; job.seq = wait_seq; job.cl = c->chunk_rows;
+      job.chunk = blk + 1; job.rank = (uint32_t)c->rank; job.nctas = (uint32_t)c->sm_count;
+    }
     const int acc = blk > 0, fin = blk + 1 == c->ncolblk;
     // pass `blk` gathers from chunk `blk` of the gathered vector only: wait for exactly that piece of the all-gather
     if (c->chunks_in_flight) LZ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_chunk[blk], 0));
@@ -754,9 +820,10 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
       if (grid > need) grid = need;
       if (grid < 1) grid = 1;
       LZ_TRY(ensure_partials(c, grid));
+      grid += job.nctas;
       k_spmv_sell<<<grid, kBlock, 0, c->stream>>>(c->sell_sp + (uint64_t)blk * c->n_items, c->sell_col, c->n_long, c->n_items,
                                                   (uint32_t)c->n_loc, x_gather, q_local, w_out, c->partials, c->ticket + 0, alpha_out, acc, fin,
-                                                  c->flags, blk, (uint32_t)c->world, wait_seq);
+                                                  c->flags, blk, (uint32_t)c->world, wait_seq, job);
     } else {                                         // CSR: vector (sub-warp) per row by degree bin, or warp per row
       const lz_spmv_plan& plan = (c->spmv_variant == LZ_SPMV_WARP) ? c->plan_warp : c->plan_auto[blk];
       if (plan.nitems == 0) return lz_fail(LZ_ERR_ARG, "empty SpMV plan");
@@ -788,14 +855,15 @@ int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, 
   return LZ_OK;
 }
 
-int lz_k_scale_push(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* beta_out, unsigned long long seq) {
+int lz_k_scale_push(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* beta_out, unsigned long long seq,
+                    uint32_t push_chunks) {
   lz_peers peers;
   for (int r = 0; r < LZ_MAX_WORLD; r++) { peers.x[r] = c->peer_xfull[r]; peers.f[r] = c->peer_flags[r]; }
   // few CTAs suffice to saturate NVLink; cap so the per-chunk ticketing stays cheap
   unsigned g = stream_grid(c, c->chunk_rows / 2 + 1);
   const unsigned cap = (unsigned)c->sm_count * 2;
   if (g > cap) g = cap;
-  k_scale_push<<<g, kBlock, 0, c->stream>>>(w, norm2, c->n_loc, q_next, peers, c->chunk_rows, c->ncolblk, (uint32_t)c->world,
+  k_scale_push<<<g, kBlock, 0, c->stream>>>(w, norm2, c->n_loc, q_next, peers, c->chunk_rows, c->ncolblk, push_chunks, (uint32_t)c->world,
                                             (uint32_t)c->rank, seq, c->push_ticket, beta_out);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
