@@ -40,7 +40,9 @@ WORKLOADS = {
 }
 
 
-def make_spec(lz, w, scale_override=None):
+def make_spec(lz, w, scale_override=None, n_override=None):
+    if n_override:
+        w = dict(w, n=n_override)
     if w["kind"] == "rmat":
         return lz.GraphSpec.rmat(scale_override or w["scale"], w["ef"], w["seed"])
     if w["kind"] == "er":
@@ -148,6 +150,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=int, default=None, help="override the R-MAT scale (debug)")
     ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--n", type=int, default=None, help="override n of the ER / banded workloads (debug)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reorth-detail", action="store_true")
@@ -169,7 +172,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        spec = make_spec(lz, w, args.scale)
+        spec = make_spec(lz, w, args.scale, args.n)
         csr_path = os.path.join(tempfile.gettempdir(), f"lz_bench_{args.workload}_{args.scale or ''}.bin")
         try:
             with lz.Context(local_rank) as ctx:           # input construction only (not timed, not on the measured path)
@@ -221,7 +224,7 @@ def main():
         return float(t.item())
 
     ctx = lz.Context(local_rank, rank, world, uid)
-    spec = make_spec(lz, w, args.scale)
+    spec = make_spec(lz, w, args.scale, args.n)
     t0 = time.perf_counter()
     ctx.graph_generate(spec)
     ctx.sync()

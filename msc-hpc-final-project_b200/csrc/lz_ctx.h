@@ -89,6 +89,7 @@ struct lz_ctx {
   uint64_t chunk_rows = 0;         // cl: rows of each rank per column block; n_loc = ncolblk * cl
   uint64_t ldv = 0;                // leading dimension of V (n_loc rounded up to 32 doubles => 256-byte aligned rows)
   uint32_t max_degree = 0;
+  bool natural_order = false;      // vertex order kept (band-like, unskewed graphs) instead of degree-sorted
   uint64_t empty_rows = 0;
   uint32_t* orig_ro = nullptr;     // device, original-order full CSR (kept for lz_csr_download)
   uint32_t* orig_ci = nullptr;

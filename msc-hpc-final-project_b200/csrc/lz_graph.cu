@@ -58,6 +58,24 @@ __global__ void k_degree_keys(const uint32_t* __restrict__ ro, uint64_t n, uint3
   val[v] = (uint32_t)v;
 }
 
+__global__ void k_iota_u32(uint32_t* p, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (uint32_t)i;
+}
+
+// number of stored entries whose column is within `radius` of the row (how band-like the natural numbering is)
+__global__ void k_locality(const uint32_t* __restrict__ ro, const uint32_t* __restrict__ ci, uint64_t n, uint64_t radius,
+                           unsigned long long* __restrict__ out) {
+  unsigned long long acc = 0;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
+    for (uint32_t j = ro[r]; j < ro[r + 1]; j++) {
+      const uint64_t cc = ci[j];
+      acc += (cc > r ? cc - r : r - cc) <= radius;
+    }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 __global__ void k_fill_u32(uint32_t* p, uint64_t n, uint32_t v) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -66,12 +84,14 @@ __global__ void k_fill_u32(uint32_t* p, uint64_t n, uint32_t v) {
 // sorted position s -> new id; builds old2new and new2old. Rank = s % world, local row l = s / world; the global
 // numbering is chunk-major: id = (l / cl) * (world * cl) + rank * cl + (l % cl), so chunk c of every rank's rows forms
 // one contiguous window of the gathered vector (= one column block = one piece of the pipelined all-gather).
-__global__ void k_relabel(const uint32_t* __restrict__ sorted_old, uint64_t n, uint32_t world, uint64_t cl,
+// block_rows == 0: positions are dealt cyclically (degree order); > 0: contiguous blocks of block_rows positions per rank
+// (natural order, keeps the locality of banded / mesh-like graphs).
+__global__ void k_relabel(const uint32_t* __restrict__ sorted_old, uint64_t n, uint32_t world, uint64_t cl, uint64_t block_rows,
                           uint32_t* __restrict__ old2new, uint32_t* __restrict__ new2old) {
   uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   uint32_t old = sorted_old[s];
-  const uint64_t r = s % world, l = s / world;
+  const uint64_t r = block_rows ? s / block_rows : s % world, l = block_rows ? s % block_rows : s / world;
   uint32_t nw = (uint32_t)((l / cl) * (world * cl) + r * cl + (l % cl));
   old2new[old] = nw;
   new2old[nw] = old;
@@ -79,10 +99,10 @@ __global__ void k_relabel(const uint32_t* __restrict__ sorted_old, uint64_t n, u
 
 // local row l of rank r is sorted position l*world + r
 __global__ void k_local_lengths(const uint32_t* __restrict__ sorted_old, const uint32_t* __restrict__ ro, uint64_t n, uint32_t world,
-                                uint32_t rank, uint64_t n_loc, uint32_t* __restrict__ len) {
+                                uint32_t rank, uint64_t n_loc, uint64_t block_rows, uint32_t* __restrict__ len) {
   uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= n_loc) return;
-  uint64_t s = l * world + rank;
+  uint64_t s = block_rows ? (uint64_t)rank * block_rows + l : l * world + rank;
   uint32_t d = 0;
   if (s < n) { uint32_t old = sorted_old[s]; d = ro[old + 1] - ro[old]; }
   len[l] = d;
@@ -93,11 +113,11 @@ __global__ void k_local_lengths(const uint32_t* __restrict__ sorted_old, const u
 // a block, ascending column inside a row slice.
 __global__ void k_local_keys(const uint32_t* __restrict__ sorted_old, const uint32_t* __restrict__ ro, const uint32_t* __restrict__ ci,
                              const uint32_t* __restrict__ old2new, const uint32_t* __restrict__ row_ptr, uint64_t n, uint32_t world,
-                             uint32_t rank, uint64_t n_loc, uint64_t width, int rowbits, uint64_t* __restrict__ keys) {
+                             uint32_t rank, uint64_t n_loc, uint64_t block_rows, uint64_t width, int rowbits, uint64_t* __restrict__ keys) {
   uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint32_t lane = threadIdx.x & 31;
   if (warp >= n_loc) return;
-  uint64_t s = warp * world + rank;
+  uint64_t s = block_rows ? (uint64_t)rank * block_rows + warp : warp * world + rank;
   if (s >= n) return;
   uint32_t old = sorted_old[s];
   uint32_t b = ro[old], e = ro[old + 1], dst = row_ptr[warp];
@@ -259,33 +279,14 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
   c->orig_ro = ro_d; c->orig_ci = ci_d;
   c->n = n; c->nnz = nnz;
   const uint32_t world = (uint32_t)c->world, rank = (uint32_t)c->rank;
-  // Rows per rank and column blocks. A column block (= chunk) is `cl` rows of every rank: a window of world * cl
-  // entries of the gathered vector that one SpMV pass gathers from; it is sized to stay L2-resident (64 MiB measured
-  // best on C3, profiles/), and for world > 1 it is also the unit of the pipelined all-gather.
-  uint64_t window = 64ull << 20;
-  if (const char* e = getenv("LZ_SPMV_WINDOW_MB")) { long v = atol(e); if (v >= 1) window = (uint64_t)v << 20; }
-  const uint64_t rows32 = (((n + world - 1) / world) + 31) & ~31ull;
-  uint64_t cl = (window / 8 / world) & ~31ull;
-  if (cl < 32) cl = 32;
-  if (const char* e = getenv("LZ_SPMV_COLBLOCKS")) { int v = atoi(e); if (v >= 1) cl = (((rows32 + v - 1) / v) + 31) & ~31ull; }
-  if (cl > rows32) cl = rows32;
-  uint32_t nblk = (uint32_t)((rows32 + cl - 1) / cl);
-  if (nblk > LZ_MAX_COLBLK) { cl = (((rows32 + LZ_MAX_COLBLK - 1) / LZ_MAX_COLBLK) + 31) & ~31ull; nblk = (uint32_t)((rows32 + cl - 1) / cl); }
-  while (nblk > 1 && 32 + bits_for((uint64_t)nblk * cl) + bits_for(nblk) > 64) { cl *= 2; nblk = (uint32_t)((rows32 + cl - 1) / cl); }
-  const uint64_t n_loc = (uint64_t)nblk * cl, n_pad = n_loc * world;
-  c->chunk_rows = cl;
-  if (n_pad > 0xFFFFFFFEull) return lz_fail(LZ_ERR_ARG, "n = %llu too large for 32-bit vertex ids", (unsigned long long)n);
-  c->n_loc = n_loc;
   cudaStream_t st = c->stream;
 
-  DevBuf key_in, key_out, val_in, sorted_old, old2new, len, tmp;
+  // 1. vertex order. Degree order (stable radix sort => ties keep ascending original id) by default; the natural order when
+  //    the graph is band-like and not skewed (there the original numbering already has the locality that sorting would destroy).
+  DevBuf key_in, key_out, val_in, sorted_old, old2new, len, tmp, loc_d;
   LZ_CUDA(cudaMalloc(&key_in.p, n * 4)); LZ_CUDA(cudaMalloc(&key_out.p, n * 4));
   LZ_CUDA(cudaMalloc(&val_in.p, n * 4)); LZ_CUDA(cudaMalloc(&sorted_old.p, n * 4));
-  LZ_CUDA(cudaMalloc(&old2new.p, n * 4)); LZ_CUDA(cudaMalloc(&len.p, (n_loc + 1) * 4));
-  LZ_CUDA(cudaMalloc((void**)&c->new2old, n_pad * 4));
-  LZ_CUDA(cudaMalloc((void**)&c->row_ptr, (n_loc + 1) * 4));
-
-  // 1. degree ordering (stable radix sort => ties keep ascending original id)
+  LZ_CUDA(cudaMalloc(&loc_d.p, 8));
   k_degree_keys<<<grid_for(n, 256), 256, 0, st>>>(ro_d, n, key_in.as<uint32_t>(), val_in.as<uint32_t>());
   size_t tb = 0;
   LZ_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key_in.as<uint32_t>(), key_out.as<uint32_t>(), val_in.as<uint32_t>(),
@@ -293,16 +294,52 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
   LZ_CUDA(cudaMalloc(&tmp.p, tb ? tb : 1));
   LZ_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key_in.as<uint32_t>(), key_out.as<uint32_t>(), val_in.as<uint32_t>(),
                                           sorted_old.as<uint32_t>(), (int64_t)n, 0, 32, st));
-  // max degree / isolated vertices from the sorted keys (key = ~deg, ascending)
-  uint32_t kfirst = 0;
+  uint32_t kfirst = 0;   // key = ~deg ascending: the first key belongs to the largest degree
+  unsigned long long near = 0;
+  const uint64_t radius = (n / 256 > 65536) ? n / 256 : 65536;
+  LZ_CUDA(cudaMemsetAsync(loc_d.p, 0, 8, st));
+  k_locality<<<(unsigned)c->sm_count * 8, 256, 0, st>>>(ro_d, ci_d, n, radius, (unsigned long long*)loc_d.p);
   LZ_CUDA(cudaMemcpyAsync(&kfirst, key_out.p, 4, cudaMemcpyDeviceToHost, st));
+  LZ_CUDA(cudaMemcpyAsync(&near, loc_d.p, 8, cudaMemcpyDeviceToHost, st));
+  LZ_CUDA(cudaStreamSynchronize(st));
+  c->max_degree = ~kfirst;
+  const double avg_deg = (double)nnz / (double)n;
+  bool natural = radius < n / 8 && c->max_degree <= LZ_SELL_LONG && (double)c->max_degree <= 8.0 * (avg_deg > 1.0 ? avg_deg : 1.0) &&
+                 (double)near >= 0.5 * (double)nnz;
+  if (const char* e = getenv("LZ_ORDER")) natural = (e[0] == 'n');
+  c->natural_order = natural;
+
+  // Rows per rank and column blocks. A column block (= chunk) is `cl` rows of every rank: a window of world * cl
+  // entries of the gathered vector that one SpMV pass gathers from; it is sized to stay L2-resident (64 MiB measured
+  // best on C3, profiles/), and for world > 1 it is also the unit of the pipelined exchange. With the natural order the
+  // gathers are local anyway, so one GPU uses a single block.
+  uint64_t window = 64ull << 20;
+  if (const char* e = getenv("LZ_SPMV_WINDOW_MB")) { long v = atol(e); if (v >= 1) window = (uint64_t)v << 20; }
+  const uint64_t rows32 = (((n + world - 1) / world) + 31) & ~31ull;
+  uint64_t cl = (window / 8 / world) & ~31ull;
+  if (cl < 32) cl = 32;
+  if (natural && world == 1) cl = rows32;
+  if (const char* e = getenv("LZ_SPMV_COLBLOCKS")) { int v = atoi(e); if (v >= 1) cl = (((rows32 + v - 1) / v) + 31) & ~31ull; }
+  if (cl > rows32) cl = rows32;
+  uint32_t nblk = (uint32_t)((rows32 + cl - 1) / cl);
+  if (nblk > LZ_MAX_COLBLK) { cl = (((rows32 + LZ_MAX_COLBLK - 1) / LZ_MAX_COLBLK) + 31) & ~31ull; nblk = (uint32_t)((rows32 + cl - 1) / cl); }
+  while (nblk > 1 && 32 + bits_for((uint64_t)nblk * cl) + bits_for(nblk) > 64) { cl *= 2; nblk = (uint32_t)((rows32 + cl - 1) / cl); }
+  const uint64_t n_loc = (uint64_t)nblk * cl, n_pad = n_loc * world;
+  const uint64_t block_rows = natural ? n_loc : 0;   // natural order: rank r owns positions [r * n_loc, (r + 1) * n_loc)
+  c->chunk_rows = cl;
+  if (n_pad > 0xFFFFFFFEull) return lz_fail(LZ_ERR_ARG, "n = %llu too large for 32-bit vertex ids", (unsigned long long)n);
+  c->n_loc = n_loc;
+  LZ_CUDA(cudaMalloc(&old2new.p, n * 4)); LZ_CUDA(cudaMalloc(&len.p, (n_loc + 1) * 4));
+  LZ_CUDA(cudaMalloc((void**)&c->new2old, n_pad * 4));
+  LZ_CUDA(cudaMalloc((void**)&c->row_ptr, (n_loc + 1) * 4));
+  if (natural) k_iota_u32<<<grid_for(n, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), n);
 
   // 2. relabel
   k_fill_u32<<<grid_for(n_pad, 256), 256, 0, st>>>(c->new2old, n_pad, 0xFFFFFFFFu);
-  k_relabel<<<grid_for(n, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), n, world, cl, old2new.as<uint32_t>(), c->new2old);
+  k_relabel<<<grid_for(n, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), n, world, cl, block_rows, old2new.as<uint32_t>(), c->new2old);
 
   // 3. local row pointer
-  k_local_lengths<<<grid_for(n_loc, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), ro_d, n, world, rank, n_loc, len.as<uint32_t>());
+  k_local_lengths<<<grid_for(n_loc, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), ro_d, n, world, rank, n_loc, block_rows, len.as<uint32_t>());
   LZ_CUDA(cudaMemsetAsync(len.as<uint32_t>() + n_loc, 0, 4, st));
   {
     DevBuf t2; size_t b2 = 0;
@@ -329,7 +366,6 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
     if (total > 0xFFFFFFFFull) return lz_fail(LZ_ERR_ARG, "local nnz %llu does not fit 32-bit row offsets", (unsigned long long)total);
     c->nnz_loc = total;
   }
-  c->max_degree = ~kfirst;
 
   // 4. column blocks were fixed above (nblk windows of world * cl entries)
   const int rowbits = bits_for(n_loc);
@@ -345,7 +381,7 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
     LZ_CUDA(cudaMalloc((void**)&c->seg_store, (uint64_t)nblk * (n_loc + 1) * 4));
     if (m) {
       k_local_keys<<<grid_for(n_loc * 32, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), ro_d, ci_d, old2new.as<uint32_t>(), c->row_ptr, n,
-                                                                world, rank, n_loc, width, rowbits, k_in.as<uint64_t>());
+                                                                world, rank, n_loc, block_rows, width, rowbits, k_in.as<uint64_t>());
       int end_bit = 32 + rowbits + (nblk > 1 ? bits_for(nblk) : 0);
       if (end_bit > 64) end_bit = 64;
       LZ_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, b4, k_in.as<uint64_t>(), k_out.as<uint64_t>(), (int64_t)m, 0, end_bit, st));
@@ -368,6 +404,7 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
     k_bin_bounds<<<1, 32, 0, st>>>(c->row_ptr, (uint32_t)n_loc, thr_d.as<uint32_t>(), 7, out_d.as<uint32_t>());
     LZ_CUDA(cudaMemcpyAsync(out_h, out_d.p, sizeof(out_h), cudaMemcpyDeviceToHost, st));
     LZ_CUDA(cudaStreamSynchronize(st));
+    if (natural) for (int b = 0; b < 7; b++) out_h[b] = 0;   // rows are not length-sorted: one bin, lanes from the mean length
     uint32_t bin_rows[9];
     bin_rows[0] = 0;
     for (int b = 0; b < 7; b++) bin_rows[b + 1] = out_h[b];
@@ -413,6 +450,7 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
       k_bin_bounds<<<1, 32, 0, st>>>(c->row_ptr, (uint32_t)n_loc, thr_d.as<uint32_t>(), 1, out_d.as<uint32_t>());
       LZ_CUDA(cudaMemcpyAsync(&n_long, out_d.p, 4, cudaMemcpyDeviceToHost, st));
       LZ_CUDA(cudaStreamSynchronize(st));
+      if (natural) n_long = 0;   // not length-sorted; all rows go through the 32-row slices
     }
     const uint32_t n_items = n_long + (uint32_t)((n_loc - n_long + 31) / 32);
     const uint64_t tot_items = (uint64_t)nblk * n_items;
