@@ -166,12 +166,12 @@ def main():
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     lz = graft.load_package()
-    orc = graft.load_oracle()
 
     # ---------------------------------------------------------------------------------------------- reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
+        orc = graft.load_oracle()              # the oracle is only ever loaded for the reference / cpu_baseline legs
         spec = make_spec(lz, w, args.scale, args.n)
         csr_path = os.path.join(tempfile.gettempdir(), f"lz_bench_{args.workload}_{args.scale or ''}.bin")
         try:
@@ -310,6 +310,7 @@ def main():
     # CPU baseline: the reference's own serial Lanczos on the same graph, bounded sample, rank 0, N == 1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        orc = graft.load_oracle()
         csr_path = os.path.join(tempfile.gettempdir(), f"lz_bench_{args.workload}_{os.getpid()}.bin")
         ro, ci = ctx.csr_download()
         lz.write_bin(csr_path, ro, ci)
