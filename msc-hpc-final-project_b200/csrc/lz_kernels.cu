@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell(const uint32_t* __restrict
                                                       const double* __restrict__ q, double* __restrict__ w, double* partials,
                                                       unsigned int* ticket, double* alpha_out, int accumulate, int final_pass,
                                                       const unsigned long long* flags, uint32_t blk, uint32_t world,
-                                                      unsigned long long wait_seq, const __grid_constant__ lz_push_job job) {
+                                                      unsigned long long wait_seq, const __grid_constant__ lz_push_job job,
+                                                      uint32_t group) {
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
   // Fused exchange: the first job.nctas CTAs of pass `blk` send chunk job.chunk (= blk + 1) of the new Krylov vector to
@@ -305,52 +306,95 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell(const uint32_t* __restrict
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t nwarps = nctas * kWarps;
   double d = 0.0;
-  for (uint32_t item = cta * kWarps + (threadIdx.x >> 5); item < n_items; item += nwarps) {
-    const uint32_t c0 = __ldg(sp + item), nchunk = __ldg(sp + item + 1) - c0;
-    const uint32_t* p = scol + (uint64_t)c0 * 32 + lane;
-    double acc = 0.0;
-    uint32_t j = 0;
-    for (; j + kSellU <= nchunk; j += kSellU) {
-      uint32_t cc[kSellU];
+  // Work is handed out in quads of consecutive items. Consecutive slices have similar widths (rows are length-sorted), and
+  // most slices of a sparse column block are only one or two entries wide: such a quad is processed as one batch (all
+  // index loads, then all gathers) so a warp keeps ~8 gathers per lane in flight instead of 1-2.
+  // (group = 4 on large inputs; 1 when there are too few items to keep every warp busy with quads.)
+  const uint32_t n_units = (n_items + group - 1) / group;
+  for (uint32_t unit = cta * kWarps + (threadIdx.x >> 5); unit < n_units; unit += nwarps) {
+    const uint32_t first = unit * group;
+    uint32_t off[5];
 #pragma unroll
-      for (int u = 0; u < kSellU; u++) cc[u] = __ldcs(p + (uint64_t)(j + u) * 32);
-      double vv[kSellU];
+    for (int t = 0; t < 5; t++) off[t] = (group == 4) ? __ldg(sp + min(first + t, n_items)) : 0u;
+    const uint32_t wmax = max(max(off[1] - off[0], off[2] - off[1]), max(off[3] - off[2], off[4] - off[3]));
+    if (group == 4 && wmax <= 2 && first >= n_long) {
+      uint32_t cc[4][2];
 #pragma unroll
-      for (int u = 0; u < kSellU; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? __ldg(x + cc[u]) : 0.0;
+      for (int t = 0; t < 4; t++)
 #pragma unroll
-      for (int u = 0; u < kSellU; u++) acc += vv[u];
+        for (int u = 0; u < 2; u++)
+          cc[t][u] = (off[t] + u < off[t + 1]) ? __ldcs(scol + (uint64_t)(off[t] + u) * 32 + lane) : 0xFFFFFFFFu;
+      double vv[4][2];
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int u = 0; u < 2; u++) vv[t][u] = (cc[t][u] != 0xFFFFFFFFu) ? __ldg(x + cc[t][u]) : 0.0;
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const uint32_t item = first + t;
+        const uint32_t row = n_long + (item - n_long) * 32 + lane;
+        if (item < n_items && row < n_loc) {
+          double acc = vv[t][0] + vv[t][1];
+          if (accumulate) {
+            if (final_pass || off[t + 1] > off[t]) {
+              acc += w[row];
+              w[row] = acc;
+            }
+          } else {
+            w[row] = acc;
+          }
+          if (final_pass) d += acc * q[row];
+        }
+      }
+      continue;
     }
-    if (j < nchunk) {
-      const uint32_t rem = nchunk - j;
-      uint32_t cc[kSellU];
+    for (uint32_t item = first; item < min(first + group, n_items); item++) {
+      const uint32_t c0 = __ldg(sp + item), nchunk = __ldg(sp + item + 1) - c0;
+      const uint32_t* p = scol + (uint64_t)c0 * 32 + lane;
+      double acc = 0.0;
+      uint32_t j = 0;
+      for (; j + kSellU <= nchunk; j += kSellU) {
+        uint32_t cc[kSellU];
 #pragma unroll
-      for (int u = 0; u < kSellU - 1; u++) cc[u] = (u < (int)rem) ? __ldcs(p + (uint64_t)(j + u) * 32) : 0xFFFFFFFFu;
-      double vv[kSellU];
+        for (int u = 0; u < kSellU; u++) cc[u] = __ldcs(p + (uint64_t)(j + u) * 32);
+        double vv[kSellU];
 #pragma unroll
-      for (int u = 0; u < kSellU - 1; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? __ldg(x + cc[u]) : 0.0;
+        for (int u = 0; u < kSellU; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? __ldg(x + cc[u]) : 0.0;
 #pragma unroll
-      for (int u = 0; u < kSellU - 1; u++) acc += vv[u];
-    }
-    uint32_t row;
-    bool writer;
-    if (item < n_long) {
-      acc = warp_sum(acc);
-      row = item;
-      writer = lane == 0;
-    } else {
-      row = n_long + (item - n_long) * 32 + lane;
-      writer = row < n_loc;
-    }
-    if (writer) {
-      if (accumulate) {
-        if (final_pass || nchunk) {
-          acc += w[row];
+        for (int u = 0; u < kSellU; u++) acc += vv[u];
+      }
+      if (j < nchunk) {
+        const uint32_t rem = nchunk - j;
+        uint32_t cc[kSellU];
+#pragma unroll
+        for (int u = 0; u < kSellU - 1; u++) cc[u] = (u < (int)rem) ? __ldcs(p + (uint64_t)(j + u) * 32) : 0xFFFFFFFFu;
+        double vv[kSellU];
+#pragma unroll
+        for (int u = 0; u < kSellU - 1; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? __ldg(x + cc[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kSellU - 1; u++) acc += vv[u];
+      }
+      uint32_t row;
+      bool writer;
+      if (item < n_long) {
+        acc = warp_sum(acc);
+        row = item;
+        writer = lane == 0;
+      } else {
+        row = n_long + (item - n_long) * 32 + lane;
+        writer = row < n_loc;
+      }
+      if (writer) {
+        if (accumulate) {
+          if (final_pass || nchunk) {
+            acc += w[row];
+            w[row] = acc;
+          }
+        } else {
           w[row] = acc;
         }
-      } else {
-        w[row] = acc;
+        if (final_pass) d += acc * q[row];
       }
-      if (final_pass) d += acc * q[row];
     }
   }
   if (final_pass) {
@@ -816,14 +860,15 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
     if (c->chunks_in_flight) LZ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_chunk[blk], 0));
     if (c->spmv_variant == LZ_SPMV_AUTO) {          // sliced layout: long rows warp-per-row, short rows 32 per warp
       uint32_t grid = (uint32_t)c->sm_count * c->spmv_ctas_per_sm;
-      const uint32_t need = (c->n_items + kWarps - 1) / kWarps;
+      const uint32_t group = (c->n_items >= 64u * grid * kWarps) ? 4u : 1u;   // quads only when every warp still gets >= 16 of them
+      const uint32_t need = ((c->n_items + group - 1) / group + kWarps - 1) / kWarps;
       if (grid > need) grid = need;
       if (grid < 1) grid = 1;
       LZ_TRY(ensure_partials(c, grid));
       grid += job.nctas;
       k_spmv_sell<<<grid, kBlock, 0, c->stream>>>(c->sell_sp + (uint64_t)blk * c->n_items, c->sell_col, c->n_long, c->n_items,
                                                   (uint32_t)c->n_loc, x_gather, q_local, w_out, c->partials, c->ticket + 0, alpha_out, acc, fin,
-                                                  c->flags, blk, (uint32_t)c->world, wait_seq, job);
+                                                  c->flags, blk, (uint32_t)c->world, wait_seq, job, group);
     } else {                                         // CSR: vector (sub-warp) per row by degree bin, or warp per row
       const lz_spmv_plan& plan = (c->spmv_variant == LZ_SPMV_WARP) ? c->plan_warp : c->plan_auto[blk];
       if (plan.nitems == 0) return lz_fail(LZ_ERR_ARG, "empty SpMV plan");
