@@ -83,8 +83,11 @@ int setup_peers(lz_ctx* c) {
   if (c->world == 1) return LZ_OK;
   bool want = c->world <= LZ_MAX_WORLD;
   if (const char* e = getenv("LZ_PEER_PUSH")) want = want && atoi(e) != 0;
-  LZ_CUDA(cudaMalloc((void**)&c->flags, sizeof(unsigned long long) * LZ_MAX_COLBLK * LZ_MAX_WORLD));
-  LZ_CUDA(cudaMemsetAsync(c->flags, 0, sizeof(unsigned long long) * LZ_MAX_COLBLK * LZ_MAX_WORLD, c->stream));
+  // arrival counters [LZ_MAX_COLBLK][LZ_MAX_WORLD] followed by the scalar exchange area [2 kinds][2][LZ_MAX_WORLD] x 16 B
+  const size_t flag_bytes = sizeof(unsigned long long) * LZ_MAX_COLBLK * LZ_MAX_WORLD + 16 * 2 * 2 * LZ_MAX_WORLD;
+  LZ_CUDA(cudaMalloc((void**)&c->flags, flag_bytes));
+  LZ_CUDA(cudaMemsetAsync(c->flags, 0, flag_bytes, c->stream));
+  c->red_seq = 0;
   LZ_CUDA(cudaMalloc((void**)&c->push_ticket, sizeof(unsigned int) * LZ_MAX_COLBLK));
   LZ_CUDA(cudaMemsetAsync(c->push_ticket, 0, sizeof(unsigned int) * LZ_MAX_COLBLK, c->stream));
   c->push_seq = 0;
@@ -384,6 +387,9 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
   const bool dist = c->world > 1;
   // chunk 0 of each new vector is sent by the normalisation kernel, chunk b + 1 by SpMV pass b (sliced variant only)
   bool fused_push = c->peer_push && c->spmv_variant == LZ_SPMV_AUTO && c->ncolblk > 1;
+  // plain Lanczos on the sliced variant: alpha and ||w||^2 are reduced through peer memory too (no collective launches)
+  bool peer_scalars = c->peer_push && c->spmv_variant == LZ_SPMV_AUTO && reorth == LZ_REORTH_NONE;
+  if (const char* e = getenv("LZ_PEER_SCALARS")) peer_scalars = peer_scalars && atoi(e) != 0;
   if (const char* e = getenv("LZ_FUSED_PUSH")) fused_push = fused_push && atoi(e) != 0;
   c->ev_used = 0;
   g_marks.clear();
@@ -400,14 +406,17 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
     double* qj = c->V + (uint64_t)j * ldv;
     {  // w = A q_j ; alpha_j = w . q_j                                   (cu_lanczos.cu:101-105)
       Scope s(c, 0);
-      LZ_TRY(lz_k_spmv_dot(c, dist ? c->xfull : qj, qj, c->w, c->alpha + j, c->peer_push ? c->push_seq : 0ull, fused_push ? qj : nullptr));
+      const bool last = j + 1 == k;    // the last alpha is read by nobody on the device: reduce it with NCCL into alpha[k-1]
+      LZ_TRY(lz_k_spmv_dot(c, dist ? c->xfull : qj, qj, c->w, c->alpha + j, c->peer_push ? c->push_seq : 0ull, fused_push ? qj : nullptr,
+                           (peer_scalars && !last) ? ++c->red_seq : 0ull));
     }
-    LZ_TRY(allreduce_sum(c, c->alpha + j, 1));
+    if (!peer_scalars || j + 1 == k) LZ_TRY(allreduce_sum(c, c->alpha + j, 1));
     if (j + 1 == k) break;                                               // last step needs alpha only (cu_lanczos.cu:116)
     {  // w -= alpha_j q_j ; w -= beta_{j-1} q_{j-1} ; ||w||^2             (cu_lanczos.cu:108-120)
       Scope s(c, 1);
+      const unsigned long long a_seq = peer_scalars ? c->red_seq : 0ull;   // consumes alpha (kind 0, a_seq), publishes ||w||^2 (kind 1, a_seq)
       LZ_TRY(lz_k_update_norm(c, c->w, qj, j ? qj - ldv : nullptr, c->alpha + j, j ? c->beta + (j - 1) : nullptr,
-                              reorth ? nullptr : c->scal + 1));
+                              reorth ? nullptr : c->scal + 1, a_seq));
     }
     if (reorth) {  // classical Gram-Schmidt, twice, against q_0..q_j
       Scope s(c, 3);
@@ -417,10 +426,11 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
         LZ_TRY(lz_k_combine(c, c->V, j + 1, c->hcoef, -1.0, c->w, c->w, pass == 1 ? c->scal + 1 : nullptr));
       }
     }
-    LZ_TRY(allreduce_sum(c, c->scal + 1, 1));
+    if (!peer_scalars) LZ_TRY(allreduce_sum(c, c->scal + 1, 1));
     {  // beta_j = ||w|| ; q_{j+1} = w / beta_j                            (cu_lanczos.cu:120-123)
       Scope s(c, 1);
-      if (c->peer_push) LZ_TRY(lz_k_scale_push(c, c->w, c->scal + 1, qj + ldv, c->beta + j, ++c->push_seq, fused_push ? 1u : c->ncolblk));
+      if (c->peer_push) LZ_TRY(lz_k_scale_push(c, c->w, c->scal + 1, qj + ldv, c->beta + j, ++c->push_seq, fused_push ? 1u : c->ncolblk,
+                                               peer_scalars ? c->red_seq : 0ull));
       else LZ_TRY(lz_k_scale(c, c->w, c->scal + 1, qj + ldv, dist ? c->xfull : nullptr, c->beta + j));
     }
     if (!c->peer_push) LZ_TRY(allgather_chunks(c, c->xfull, true));

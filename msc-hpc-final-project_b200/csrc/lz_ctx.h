@@ -76,6 +76,7 @@ struct lz_ctx {
   unsigned long long* flags = nullptr;                // device, [LZ_MAX_COLBLK][LZ_MAX_WORLD], written by the peers
   unsigned int* push_ticket = nullptr;                // device, [LZ_MAX_COLBLK]
   unsigned long long push_seq = 0;                    // sequence number of the last push (same on every rank)
+  unsigned long long red_seq = 0;                     // sequence number of the last peer scalar reduction
   double* gfull = nullptr;                            // device, [n_loc * world], scratch for the host-facing gathers   // ev_chunk[] were recorded for the vector the next SpMV gathers from
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;      // lz_lanczos_run
   cudaEvent_t ev_e0 = nullptr, ev_e1 = nullptr;    // lz_tridiag_expv
@@ -157,14 +158,16 @@ void lz_free_graph(lz_ctx* c);
 // lz_kernels.cu — all launches are asynchronous on c->stream
 int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out /* device scalar or null */,
                   unsigned long long wait_seq = 0 /* > 0: pass b first waits until chunk b of x_gather has arrived from every rank */,
-                  const double* push_src = nullptr /* sliced variant only: pass b also sends chunk b + 1 of this local vector */);
-int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev, const double* alpha, const double* beta_prev,
-                     double* norm2_out /* device scalar or null */);
+                  const double* push_src = nullptr /* sliced variant only: pass b also sends chunk b + 1 of this local vector */,
+                  unsigned long long red_seq = 0 /* > 0 (sliced variant): alpha partial is published to all ranks instead of stored */);
+int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev, double* alpha, const double* beta_prev,
+                     double* norm2_out /* device scalar or null */, unsigned long long red_seq = 0 /* > 0: scalars go through the peer exchange */);
 // q_next = w / sqrt(*norm2); when xfull != null also stores it into this rank's slots of the chunk-major gathered vector
 int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* xfull, double* beta_out);
 // peer exchange: q_next = w / sqrt(*norm2) (norm2 == null: plain copy of w) stored locally and into every rank's gathered vector; raises seq
 int lz_k_scale_push(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* beta_out, unsigned long long seq,
-                    uint32_t push_chunks /* chunks [0, push_chunks) are sent here; the rest by the SpMV passes */);
+                    uint32_t push_chunks /* chunks [0, push_chunks) are sent here; the rest by the SpMV passes */,
+                    unsigned long long red_seq = 0);
 // q0_local[l] = x_orig[new2old[slot(l)]] / sqrt(*norm2)
 int lz_k_permute_in_local(lz_ctx* c, const double* x_orig, const double* norm2, double* q0_local);
 // local vector <-> this rank's slots of the chunk-major gathered vector

@@ -47,10 +47,57 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
   return v;
 }
 
+// ---- scalar all-reduce over peer memory (multi-GPU, plain Lanczos) ------------------------------------------------
+// Each rank's reduction kernel publishes its partial (value, then sequence number with release semantics) in slot
+// [kind][seq & 1][rank] of EVERY rank's exchange area; the consuming kernel spins until all `world` slots carry `seq`
+// and adds them in rank order, so all ranks obtain the bit-identical sum without a collective launch in between.
+// Two parities suffice: a rank can be at most one reduction of a kind ahead of its slowest peer (the vector exchange
+// of the step in between needs every rank's contribution).
+struct lz_red_slot { double val; unsigned long long seq; };
+struct lz_red {
+  lz_red_slot* area[LZ_MAX_WORLD];   // exchange area of every rank as seen from this GPU: [2 kinds][2][LZ_MAX_WORLD]
+  unsigned long long seq;           // 0 = disabled (single GPU / NCCL path): plain device scalars are used
+  uint32_t world, rank;
+};
+__device__ __forceinline__ void red_publish(const lz_red& red, int kind, double v) {
+  const size_t idx = ((size_t)kind * 2 + (red.seq & 1)) * LZ_MAX_WORLD + red.rank;
+  for (uint32_t r = 0; r < red.world; r++) red.area[r][idx].val = v;      // all values first ...
+  __threadfence_system();                                                 // ... one fence ...
+  for (uint32_t r = 0; r < red.world; r++)                                // ... then the sequence numbers
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&red.area[r][idx].seq), "l"(red.seq) : "memory");
+}
+// All threads of the CTA call this; returns the total in every thread.
+__device__ __forceinline__ double red_consume(const lz_red& red, int kind, double* sm_bcast) {
+  if (threadIdx.x == 0) {
+    const lz_red_slot* base = red.area[red.rank] + ((size_t)kind * 2 + (red.seq & 1)) * LZ_MAX_WORLD;
+    double tot = 0.0;
+    for (uint32_t r = 0; r < red.world; r++) {
+      unsigned long long got, t0 = 0;
+      unsigned int spins = 0;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&base[r].seq) : "memory");
+        if (got >= red.seq) break;
+        __nanosleep(32);
+        if ((++spins & 0xFFFFu) == 0) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 20000000000ull) __trap();
+        }
+      }
+      tot += *reinterpret_cast<const volatile double*>(&base[r].val);
+    }
+    *sm_bcast = tot;
+  }
+  __syncthreads();
+  return *sm_bcast;
+}
+
 // Deterministic grid reduction tail. Thread 0 of every CTA passes its CTA value; the last CTA to arrive sums all
 // `gridDim.x` partials in index order (strided per thread, then a fixed tree) and stores op(sum) to *out.
 __device__ __forceinline__ void grid_sum_finish(double cta_val, double* partials, unsigned int* ticket, double* out, double* sm,
-                                                bool* s_last, unsigned int cta = 0xFFFFFFFFu, unsigned int nctas = 0) {
+                                                bool* s_last, unsigned int cta = 0xFFFFFFFFu, unsigned int nctas = 0,
+                                                const lz_red* red = nullptr, int kind = 0) {
   if (cta == 0xFFFFFFFFu) { cta = blockIdx.x; nctas = gridDim.x; }   // default: every CTA of the grid takes part
   if (threadIdx.x == 0) {
     partials[cta] = cta_val;
@@ -65,7 +112,8 @@ __device__ __forceinline__ void grid_sum_finish(double cta_val, double* partials
     for (unsigned int i = threadIdx.x; i < nctas; i += kBlock) acc += __ldcg(partials + i);
     acc = block_sum(acc, sm);
     if (threadIdx.x == 0) {
-      *out = acc;
+      if (red && red->seq) red_publish(*red, kind, acc);   // multi-GPU: the partial goes to every rank's exchange area
+      else *out = acc;
       *ticket = 0u;
     }
   }
@@ -291,7 +339,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell(const uint32_t* __restrict
                                                       unsigned int* ticket, double* alpha_out, int accumulate, int final_pass,
                                                       const unsigned long long* flags, uint32_t blk, uint32_t world,
                                                       unsigned long long wait_seq, const __grid_constant__ lz_push_job job,
-                                                      uint32_t group) {
+                                                      uint32_t group, const __grid_constant__ lz_red red) {
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
   // Fused exchange: the first job.nctas CTAs of pass `blk` send chunk job.chunk (= blk + 1) of the new Krylov vector to
@@ -399,7 +447,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell(const uint32_t* __restrict
   }
   if (final_pass) {
     d = block_sum(d, sm);
-    grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last, cta, nctas);
+    grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last, cta, nctas, &red, 0);
   }
 }
 
@@ -407,10 +455,18 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell(const uint32_t* __restrict
 // w <- (w - alpha q_j) - beta_prev q_prev, partial of ||w||^2. Same operation order as lanczos.cu:36-43.
 __global__ void __launch_bounds__(kBlock) k_update_norm(double* __restrict__ w, const double* __restrict__ qj, const double* __restrict__ qp,
                                                         const double* __restrict__ alpha_p, const double* __restrict__ beta_p,
-                                                        uint64_t n, double* partials, unsigned int* ticket, double* norm2_out) {
+                                                        uint64_t n, double* partials, unsigned int* ticket, double* norm2_out,
+                                                        const __grid_constant__ lz_red red, double* alpha_store) {
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
-  const double a = *alpha_p;
+  __shared__ double s_bcast;
+  double a;
+  if (red.seq) {                       // alpha_j = sum over ranks of the SpMV kernels' partials (peer exchange)
+    a = red_consume(red, 0, &s_bcast);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *alpha_store = a;
+  } else {
+    a = *alpha_p;
+  }
   const double b = qp ? *beta_p : 0.0;
   const uint64_t n2 = n >> 1;
   double acc = 0.0;
@@ -438,7 +494,7 @@ __global__ void __launch_bounds__(kBlock) k_update_norm(double* __restrict__ w, 
     acc += t * t;
   }
   acc = block_sum(acc, sm);
-  if (norm2_out) grid_sum_finish(acc, partials, ticket, norm2_out, sm, &s_last);
+  if (norm2_out) grid_sum_finish(acc, partials, ticket, norm2_out, sm, &s_last, 0xFFFFFFFFu, 0, &red, 1);
 }
 
 // Index of local row l in the chunk-major gathered vector (see k_relabel in lz_graph.cu).
@@ -473,8 +529,10 @@ __global__ void __launch_bounds__(kBlock) k_scale(const double* __restrict__ w, 
 __global__ void __launch_bounds__(kBlock) k_scale_push(const double* __restrict__ w, const double* __restrict__ norm2_p, uint64_t n,
                                                        double* __restrict__ q_next, const __grid_constant__ lz_peers peers, uint64_t cl,
                                                        uint32_t nchunks, uint32_t push_chunks, uint32_t world, uint32_t rank,
-                                                       unsigned long long seq, unsigned int* ticket, double* beta_out) {
-  const double beta = norm2_p ? sqrt(*norm2_p) : 1.0;
+                                                       unsigned long long seq, unsigned int* ticket, double* beta_out,
+                                                       const __grid_constant__ lz_red red) {
+  __shared__ double s_bcast;
+  const double beta = norm2_p ? sqrt(red.seq ? red_consume(red, 1, &s_bcast) : *norm2_p) : 1.0;
   if (blockIdx.x == 0 && threadIdx.x == 0 && beta_out) *beta_out = beta;
   const double2* w2 = reinterpret_cast<const double2*>(w);
   double2* q2 = reinterpret_cast<double2*>(q_next);
@@ -845,8 +903,19 @@ static int ensure_partials(lz_ctx* c, uint64_t count) {
   return LZ_OK;
 }
 
+static lz_red make_red(const lz_ctx* c, unsigned long long seq) {
+  lz_red red;
+  memset(&red, 0, sizeof(red));
+  red.seq = seq; red.world = (uint32_t)c->world; red.rank = (uint32_t)c->rank;
+  if (seq)
+    for (int r = 0; r < LZ_MAX_WORLD; r++)
+      red.area[r] = c->peer_flags[r] ? reinterpret_cast<lz_red_slot*>(c->peer_flags[r] + (size_t)LZ_MAX_COLBLK * LZ_MAX_WORLD) : nullptr;
+  return red;
+}
+
 int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out, unsigned long long wait_seq,
-                  const double* push_src) {
+                  const double* push_src, unsigned long long red_seq) {
+  const lz_red red = make_red(c, red_seq);
   for (uint32_t blk = 0; blk < c->ncolblk; blk++) {
     lz_push_job job;
     memset(&job, 0, sizeof(job));
@@ -868,7 +937,7 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
       grid += job.nctas;
       k_spmv_sell<<<grid, kBlock, 0, c->stream>>>(c->sell_sp + (uint64_t)blk * c->n_items, c->sell_col, c->n_long, c->n_items,
                                                   (uint32_t)c->n_loc, x_gather, q_local, w_out, c->partials, c->ticket + 0, alpha_out, acc, fin,
-                                                  c->flags, blk, (uint32_t)c->world, wait_seq, job, group);
+                                                  c->flags, blk, (uint32_t)c->world, wait_seq, job, group, red);
     } else {                                         // CSR: vector (sub-warp) per row by degree bin, or warp per row
       const lz_spmv_plan& plan = (c->spmv_variant == LZ_SPMV_WARP) ? c->plan_warp : c->plan_auto[blk];
       if (plan.nitems == 0) return lz_fail(LZ_ERR_ARG, "empty SpMV plan");
@@ -884,11 +953,12 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
   return LZ_OK;
 }
 
-int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev, const double* alpha, const double* beta_prev,
-                     double* norm2_out) {
+int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev, double* alpha, const double* beta_prev,
+                     double* norm2_out, unsigned long long red_seq) {
   unsigned g = stream_grid(c, c->n_loc / 2 + 1);
   LZ_TRY(ensure_partials(c, g));
-  k_update_norm<<<g, kBlock, 0, c->stream>>>(w, qj, qprev, alpha, beta_prev, c->n_loc, c->partials, c->ticket + 1, norm2_out);
+  k_update_norm<<<g, kBlock, 0, c->stream>>>(w, qj, qprev, alpha, beta_prev, c->n_loc, c->partials, c->ticket + 1, norm2_out,
+                                             make_red(c, red_seq), alpha);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
@@ -901,7 +971,7 @@ int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, 
 }
 
 int lz_k_scale_push(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* beta_out, unsigned long long seq,
-                    uint32_t push_chunks) {
+                    uint32_t push_chunks, unsigned long long red_seq) {
   lz_peers peers;
   for (int r = 0; r < LZ_MAX_WORLD; r++) { peers.x[r] = c->peer_xfull[r]; peers.f[r] = c->peer_flags[r]; }
   // few CTAs suffice to saturate NVLink; cap so the per-chunk ticketing stays cheap
@@ -909,7 +979,7 @@ int lz_k_scale_push(lz_ctx* c, const double* w, const double* norm2, double* q_n
   const unsigned cap = (unsigned)c->sm_count * 2;
   if (g > cap) g = cap;
   k_scale_push<<<g, kBlock, 0, c->stream>>>(w, norm2, c->n_loc, q_next, peers, c->chunk_rows, c->ncolblk, push_chunks, (uint32_t)c->world,
-                                            (uint32_t)c->rank, seq, c->push_ticket, beta_out);
+                                            (uint32_t)c->rank, seq, c->push_ticket, beta_out, make_red(c, red_seq));
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
