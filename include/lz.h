@@ -123,6 +123,9 @@ int lz_tridiag_expv(lz_ctx* ctx);
 /* Optional read-back: eigenvalues ascending [k], eigenvectors row-major [k*k] with eigvecs[i*k+j] = component i of
  * vector j (the LAPACK_ROW_MAJOR layout eigen.cu:20 produces), coeff [k]. Synchronises. Any pointer may be NULL. */
 int lz_get_eigen(lz_ctx* ctx, double* eigvals_out, double* eigvecs_out, double* coeff_out);
+/* Convergence estimate: relative 2-norm change of e^A x between Krylov dimensions k_prev < k (k = the last run), from the
+ * tridiagonal alone (no pass over the basis). The reference has no such check; its author recommends one (writeup sec. 11). */
+int lz_estimate_change(lz_ctx* ctx, uint32_t k_prev, double* rel_out);
 /* ans = V * c as a tall-skinny GEMV on the device. Replaces multOut's cblas_dgemv (multiplyOut.cu:43-47) and
  * cu_multOut's cublasDgemv (parallel-mult-on-card/lib/cu_multiplyOut.cu:66-72). Enqueue only. */
 int lz_multout(lz_ctx* ctx);

@@ -91,6 +91,7 @@ _sig("lz_lanczos_run", _ctx, C.c_uint32, C.c_int)
 _sig("lz_get_tridiag", _ctx, _f64p, _f64p)
 _sig("lz_tridiag_expv", _ctx)
 _sig("lz_get_eigen", _ctx, _f64p, _f64p, _f64p)
+_sig("lz_estimate_change", _ctx, C.c_uint32, _P(C.c_double))
 _sig("lz_multout", _ctx)
 _sig("lz_get_ans", _ctx, _f64p)
 _sig("lz_expv_host", _ctx, _f64p, C.c_uint32, C.c_int, _f64p)
@@ -258,6 +259,11 @@ class Context:
         w, z, c = np.empty(k), np.empty((k, k)), np.empty(k)
         _check(lib.lz_get_eigen(self._h, _f64(w), _f64(z), _f64(c)))
         return w, z, c
+
+    def estimate_change(self, k_prev):
+        r = C.c_double(0)
+        _check(lib.lz_estimate_change(self._h, k_prev, C.byref(r)))
+        return r.value
 
     def multout(self):
         _check(lib.lz_multout(self._h))

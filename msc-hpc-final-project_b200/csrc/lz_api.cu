@@ -485,6 +485,44 @@ extern "C" int lz_get_eigen(lz_ctx* c, double* eigvals_out, double* eigvecs_out,
   return LZ_OK;
 }
 
+// A-posteriori convergence estimate (the author's own recommendation, writeup section 11): with an orthonormal basis,
+// || y_k - y_k' ||_2 = || c_k - [c_k'; 0] ||_2, so the change of the answer between Krylov dimensions k' < k costs two
+// k x k eigen-solves and no pass over the basis.
+extern "C" int lz_estimate_change(lz_ctx* c, uint32_t k_prev, double* rel_out) {
+  if (!c || !rel_out) return lz_fail(LZ_ERR_ARG, "null argument");
+  if (!c->have_tridiag) return lz_fail(LZ_ERR_ARG, "lz_lanczos_run must be called before lz_estimate_change");
+  const uint32_t k = c->k_done;
+  if (k_prev < 1 || k_prev >= k) return lz_fail(LZ_ERR_ARG, "k_prev must be in [1, %u)", k);
+  LZ_TRY(set_dev(c));
+  double *ev = nullptr, *evec = nullptr, *work = nullptr, *coef = nullptr;
+  int* st = nullptr;
+  LZ_CUDA(cudaMalloc((void**)&ev, k * 8)); LZ_CUDA(cudaMalloc((void**)&evec, (size_t)k * k * 8));
+  LZ_CUDA(cudaMalloc((void**)&work, (size_t)k * k * 8)); LZ_CUDA(cudaMalloc((void**)&coef, 2 * k * 8));
+  LZ_CUDA(cudaMalloc((void**)&st, 2 * sizeof(int)));
+  std::vector<double> a(k), b(k_prev);
+  int sth[2] = {0, 0};
+  int rc = LZ_OK;
+  do {
+    if ((rc = lz_k_tridiag_expv_into(c, k, ev, evec, work, coef, st)) != LZ_OK) break;
+    if ((rc = lz_k_tridiag_expv_into(c, k_prev, ev, evec, work, coef + k, st + 1)) != LZ_OK) break;
+    if (cudaMemcpyAsync(a.data(), coef, k * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaMemcpyAsync(b.data(), coef + k, k_prev * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaMemcpyAsync(sth, st, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = lz_fail(LZ_ERR_CUDA, "read-back of the coefficient vectors failed"); break; }
+  } while (0);
+  cudaFree(ev); cudaFree(evec); cudaFree(work); cudaFree(coef); cudaFree(st);
+  if (rc != LZ_OK) return rc;
+  if (sth[0] || sth[1]) return lz_fail(LZ_ERR_NUMERIC, "tridiagonal solve failed or overflowed (status %d / %d)", sth[0], sth[1]);
+  double num = 0.0, den = 0.0;
+  for (uint32_t i = 0; i < k; i++) {
+    const double d = a[i] - (i < k_prev ? b[i] : 0.0);
+    num += d * d;
+    den += a[i] * a[i];
+  }
+  *rel_out = den > 0.0 ? sqrt(num / den) : 0.0;
+  return LZ_OK;
+}
+
 extern "C" int lz_multout(lz_ctx* c) {
   if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
   if (!c->have_coef) return lz_fail(LZ_ERR_ARG, "lz_tridiag_expv must be called before lz_multout");

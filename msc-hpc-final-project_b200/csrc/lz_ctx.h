@@ -178,6 +178,7 @@ int lz_k_multidot(lz_ctx* c, const double* V, uint32_t nvec, const double* w, do
 int lz_k_combine(lz_ctx* c, const double* V, uint32_t nvec, const double* coef, double coef_sign, const double* base, double* out,
                  double* norm2_out /* device scalar or null */);
 int lz_k_tridiag_expv(lz_ctx* c, uint32_t k);
+int lz_k_tridiag_expv_into(lz_ctx* c, uint32_t k, double* eigvals, double* eigvecs, double* work, double* coef, int* status);
 // dst[i] = x_orig[new2old[first + i]] (/ sqrt(*norm2) when norm2 != null), i < count; padding slots -> 0
 int lz_k_permute_in(lz_ctx* c, const double* x_orig, const double* norm2, uint64_t first, uint64_t count, double* dst);
 int lz_k_permute_out(lz_ctx* c, const double* y_new_full, double* y_orig);

@@ -1035,6 +1035,17 @@ int lz_k_combine(lz_ctx* c, const double* V, uint32_t nvec, const double* coef, 
   return LZ_OK;
 }
 
+// Same solve for the leading k x k block into caller-provided scratch (convergence estimate; nothing of the ctx's result is touched).
+int lz_k_tridiag_expv_into(lz_ctx* c, uint32_t k, double* eigvals, double* eigvecs, double* work, double* coef, int* status) {
+  if (k > (uint32_t)kEigMax) return lz_fail(LZ_ERR_ARG, "krylov dimension %u exceeds the on-device eigensolver limit %d", k, kEigMax);
+  const size_t zt_bytes = (size_t)k * k * sizeof(double);
+  const int in_smem = zt_bytes <= 180 * 1024;
+  if (in_smem) LZ_CUDA(cudaFuncSetAttribute(k_tridiag_expv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zt_bytes));
+  k_tridiag_expv<<<1, kBlock, in_smem ? zt_bytes : 0, c->stream>>>(k, c->alpha, c->beta, c->scal + 2, eigvals, eigvecs, work, coef, status, in_smem);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
 int lz_k_tridiag_expv(lz_ctx* c, uint32_t k) {
   if (k > (uint32_t)kEigMax) return lz_fail(LZ_ERR_ARG, "krylov dimension %u exceeds the on-device eigensolver limit %d", k, kEigMax);
   const size_t zt_bytes = (size_t)k * k * sizeof(double);

@@ -18,3 +18,20 @@ def test_row_sharded_parity(lz, world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert f"DIST_OK {world}" in r.stdout
+
+
+def test_cpp_driver_threads_per_gpu(lz, tmp_path):
+    """lib/final --gpus 2: one host thread per GPU in ONE process (peer access instead of CUDA IPC), checked against the oracle."""
+    import numpy as np
+    import oracle as orc
+    if lz.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    libdir = os.path.join(ROOT, "msc-hpc-final-project_b200", "lib")
+    subprocess.check_call(["make", "-s", "-C", libdir])
+    n, ro, ci = lz.generate_host(lz.GraphSpec.rmat(15, 8, 1))
+    ref, _, _ = orc.expv(ro, ci, 25, np.ones(n))
+    ans = str(tmp_path / "ref.f64")
+    ref.tofile(ans)
+    r = subprocess.run([os.path.join(libdir, "final"), "--graph", "rmat", "--scale", "15", "--ef", "8", "--seed", "1", "-k", "25",
+                        "--gpus", "2", "--check", ans], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -306,3 +306,20 @@ def test_band_like_graph_keeps_natural_order_and_is_fast_path(lz, orc):
         y = c.expv_host(None, 30)
     ref, _, _ = orc.expv(ro, ci, 30, np.ones(n))
     assert rel2(y, ref) < TOL
+
+
+def test_convergence_estimate_matches_actual_change(lz, orc, golden, ctx):
+    """lz_estimate_change(k') = ||y_k - y_k'|| / ||y_k|| from the tridiagonal alone; compare with the change actually
+    observed between two full runs (oracle-side check: the same quantity from the CPU restatement)."""
+    g = golden("c1_er_n10000_k20")
+    ro, ci, n = g["row_offset"], g["col_idx"], int(g["n"])
+    ctx.csr_upload(ro, ci)
+    y20 = ctx.expv_host(None, 20)
+    est = {kp: ctx.estimate_change(kp) for kp in (8, 12, 16)}
+    for kp, e in est.items():
+        ykp, _, _ = orc.expv(ro, ci, kp, np.ones(n))
+        actual = rel2(ykp, y20)
+        assert e == pytest.approx(actual, rel=1e-3, abs=1e-13), (kp, e, actual)
+    assert est[8] > est[12] > est[16]
+    with pytest.raises(lz.LzError):
+        ctx.estimate_change(20)
