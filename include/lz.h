@@ -107,7 +107,8 @@ int lz_csr_download(lz_ctx* ctx, uint32_t* row_offset_out, uint32_t* col_idx_out
 
 /* ---- hot path ---------------------------------------------------------------------------------------------------- */
 #define LZ_REORTH_NONE 0  /* plain three-term recurrence == reference (cu_lanczos.cu:97-128)                 */
-#define LZ_REORTH_FULL 1  /* every step, against all stored basis vectors, classical Gram-Schmidt applied twice */
+#define LZ_REORTH_FULL 1  /* every step, against all stored basis vectors: classical Gram-Schmidt, repeated when the first
+                             pass removed more than half of ||w||^2 ("twice is enough", decided on the device)        */
 
 /* x (n doubles, original order; NULL = all ones as in main.cu:79) -> device, computes ||x|| (cu_lanczos.h:18-24,63). */
 int lz_set_start_vector(lz_ctx* ctx, const double* x_host);
@@ -157,6 +158,7 @@ typedef struct lz_timings {
   float reorth_ms_total;/* total device time spent in reorthogonalisation kernels (profiling on)             */
   uint32_t spmv_launches;
   uint32_t kernel_launches; /* kernels of this library launched on this ctx since lz_create (cumulative)           */
+  uint32_t reorth_second_passes; /* steps of the last run whose Gram-Schmidt pass had to be repeated (LZ_REORTH_FULL)  */
 } lz_timings;
 /* profiling on => event pairs around the per-step launches (adds ~2 us per event). Off by default. */
 int lz_set_profiling(lz_ctx* ctx, int on);

@@ -52,7 +52,8 @@ class GraphInfo(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("lanczos_ms", C.c_float), ("tridiag_ms", C.c_float), ("multout_ms", C.c_float),
                 ("spmv_ms_avg", C.c_float), ("update_ms_avg", C.c_float), ("comm_ms_avg", C.c_float),
-                ("reorth_ms_total", C.c_float), ("spmv_launches", C.c_uint32), ("kernel_launches", C.c_uint32)]
+                ("reorth_ms_total", C.c_float), ("spmv_launches", C.c_uint32), ("kernel_launches", C.c_uint32),
+                ("reorth_second_passes", C.c_uint32)]
 
 
 _P = C.POINTER

@@ -283,8 +283,8 @@ static int create_common(int device, int rank, int world, const void* uid, lz_ct
   LZ_CUDA(cudaMemset(c->scal, 0, 16 * 8));
   LZ_CUDA(cudaMalloc((void**)&c->ticket, 16 * sizeof(unsigned int)));
   LZ_CUDA(cudaMemset(c->ticket, 0, 16 * sizeof(unsigned int)));
-  LZ_CUDA(cudaMalloc((void**)&c->status, sizeof(int)));
-  LZ_CUDA(cudaMemset(c->status, 0, sizeof(int)));
+  LZ_CUDA(cudaMalloc((void**)&c->status, 4 * sizeof(int)));
+  LZ_CUDA(cudaMemset(c->status, 0, 4 * sizeof(int)));
   if (world > 1) {
     if (!uid) return lz_fail(LZ_ERR_ARG, "world > 1 needs an NCCL unique id");
     ncclUniqueId id;
@@ -393,6 +393,7 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
   if (const char* e = getenv("LZ_FUSED_PUSH")) fused_push = fused_push && atoi(e) != 0;
   c->ev_used = 0;
   g_marks.clear();
+  LZ_CUDA(cudaMemsetAsync(c->status + 2, 0, sizeof(int), c->stream));
   LZ_CUDA(cudaEventRecord(c->ev_a, c->stream));
   if (dist) {   // q_0 into the gathered buffer (a previous run left q_{k-1} there)
     if (c->peer_push) {
@@ -416,17 +417,26 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
       Scope s(c, 1);
       const unsigned long long a_seq = peer_scalars ? c->red_seq : 0ull;   // consumes alpha (kind 0, a_seq), publishes ||w||^2 (kind 1, a_seq)
       LZ_TRY(lz_k_update_norm(c, c->w, qj, j ? qj - ldv : nullptr, c->alpha + j, j ? c->beta + (j - 1) : nullptr,
-                              reorth ? nullptr : c->scal + 1, a_seq));
+                              reorth ? c->scal + 3 : c->scal + 1, a_seq));
     }
-    if (reorth) {  // classical Gram-Schmidt, twice, against q_0..q_j
+    if (reorth) {
+      // Full reorthogonalisation against q_0..q_j: classical Gram-Schmidt, repeated only when the first pass removed more
+      // than half of ||w||^2 ("twice is enough"); the decision is taken on the device.
       Scope s(c, 3);
-      for (int pass = 0; pass < 2; pass++) {
-        LZ_TRY(lz_k_multidot(c, c->V, j + 1, c->w, c->hcoef));
-        LZ_TRY(allreduce_sum(c, c->hcoef, j + 1));
-        LZ_TRY(lz_k_combine(c, c->V, j + 1, c->hcoef, -1.0, c->w, c->w, pass == 1 ? c->scal + 1 : nullptr));
-      }
+      int* skip = c->status + 1;
+      LZ_TRY(allreduce_sum(c, c->scal + 3, 1));                                   // ||w||^2 before
+      LZ_TRY(lz_k_multidot(c, c->V, j + 1, c->w, c->hcoef));
+      LZ_TRY(allreduce_sum(c, c->hcoef, j + 1));
+      LZ_TRY(lz_k_combine(c, c->V, j + 1, c->hcoef, -1.0, c->w, c->w, c->scal + 1));
+      LZ_TRY(allreduce_sum(c, c->scal + 1, 1));                                   // ||w||^2 after pass 1
+      LZ_TRY(lz_k_reorth_decide(c, c->scal + 3, c->scal + 1, skip, reinterpret_cast<unsigned int*>(c->status + 2)));
+      LZ_TRY(lz_k_multidot(c, c->V, j + 1, c->w, c->hcoef, skip));
+      LZ_TRY(allreduce_sum(c, c->hcoef, j + 1));
+      LZ_TRY(lz_k_combine(c, c->V, j + 1, c->hcoef, -1.0, c->w, c->w, c->scal + 4, skip));
+      LZ_TRY(allreduce_sum(c, c->scal + 4, 1));
+      LZ_TRY(lz_k_reorth_select(c, skip, c->scal + 4, c->scal + 1));
     }
-    if (!peer_scalars) LZ_TRY(allreduce_sum(c, c->scal + 1, 1));
+    if (!peer_scalars && !reorth) LZ_TRY(allreduce_sum(c, c->scal + 1, 1));
     {  // beta_j = ||w|| ; q_{j+1} = w / beta_j                            (cu_lanczos.cu:120-123)
       Scope s(c, 1);
       if (c->peer_push) LZ_TRY(lz_k_scale_push(c, c->w, c->scal + 1, qj + ldv, c->beta + j, ++c->push_seq, fused_push ? 1u : c->ncolblk,
@@ -622,6 +632,10 @@ extern "C" int lz_timings_get(lz_ctx* c, lz_timings* out) {
   c->tm.comm_ms_avg = (float)(sum[2] / steps);
   c->tm.reorth_ms_total = (float)sum[3];
   c->tm.kernel_launches = c->launches;
+  {
+    unsigned int sp = 0;
+    if (cudaMemcpy(&sp, c->status + 2, sizeof(sp), cudaMemcpyDeviceToHost) == cudaSuccess) c->tm.reorth_second_passes = sp;
+  }
   *out = c->tm;
   return LZ_OK;
 }

@@ -138,7 +138,7 @@ struct lz_ctx {
   double* eigvecs = nullptr;       // device, [k_cap * k_cap] (row-major, dstevd layout), + scratch of same size
   double* eigwork = nullptr;
   double* coef = nullptr;          // device, [k_cap]
-  int* status = nullptr;           // device, eigensolver status
+  int* status = nullptr;           // device: [0] eigensolver status, [1] reorth skip flag, [2] second-pass counter
   bool have_x = false, have_tridiag = false, have_coef = false, have_ans = false;
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
@@ -174,9 +174,11 @@ int lz_k_permute_in_local(lz_ctx* c, const double* x_orig, const double* norm2, 
 int lz_k_spread(lz_ctx* c, const double* local, double* xfull);
 int lz_k_collect(lz_ctx* c, const double* xfull, double* local);
 int lz_k_norm2(lz_ctx* c, const double* v, uint64_t len, double* out);
-int lz_k_multidot(lz_ctx* c, const double* V, uint32_t nvec, const double* w, double* h_out /* device [nvec] */);
+int lz_k_multidot(lz_ctx* c, const double* V, uint32_t nvec, const double* w, double* h_out /* device [nvec] */, const int* skip = nullptr);
 int lz_k_combine(lz_ctx* c, const double* V, uint32_t nvec, const double* coef, double coef_sign, const double* base, double* out,
-                 double* norm2_out /* device scalar or null */);
+                 double* norm2_out /* device scalar or null */, const int* skip = nullptr);
+int lz_k_reorth_decide(lz_ctx* c, const double* norm2_before, const double* norm2_after, int* skip, unsigned int* second_passes);
+int lz_k_reorth_select(lz_ctx* c, const int* skip, const double* norm2_second, double* norm2);
 int lz_k_tridiag_expv(lz_ctx* c, uint32_t k);
 int lz_k_tridiag_expv_into(lz_ctx* c, uint32_t k, double* eigvals, double* eigvecs, double* work, double* coef, int* status);
 // dst[i] = x_orig[new2old[first + i]] (/ sqrt(*norm2) when norm2 != null), i < count; padding slots -> 0

@@ -20,6 +20,7 @@
 #include "lz_ctx.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -630,9 +631,11 @@ __global__ void k_permute_out(const double* __restrict__ y_new, const uint32_t* 
 // (+1/TILE traffic) while TILE independent 16-byte loads per thread are in flight.
 constexpr int kDotTile = 8;
 __global__ void __launch_bounds__(kBlock) k_multidot(const double* __restrict__ V, uint64_t ldv, uint32_t nvec, const double* __restrict__ w,
-                                                     uint64_t n, double* partials /* [nvec][grid] */, unsigned int* ticket, double* h_out) {
+                                                     uint64_t n, double* partials /* [nvec][grid] */, unsigned int* ticket, double* h_out,
+                                                     const int* __restrict__ skip) {
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
+  if (skip && *skip) return;   // second Gram-Schmidt pass not needed (decided on the device, see k_reorth_decide)
   const uint64_t n2 = n >> 1;
   const double2* w2 = reinterpret_cast<const double2*>(w);
   for (uint32_t t0 = 0; t0 < nvec; t0 += kDotTile) {
@@ -697,10 +700,11 @@ __global__ void __launch_bounds__(kBlock) k_multidot(const double* __restrict__ 
 // row-major Trans dgemv, multiplyOut.cu:44). Optional partial of ||out||^2.
 __global__ void __launch_bounds__(kBlock) k_combine(const double* __restrict__ V, uint64_t ldv, uint32_t nvec, const double* __restrict__ coef,
                                                     double sign, const double* base, double* out, uint64_t n, double* partials,
-                                                    unsigned int* ticket, double* norm2_out) {
+                                                    unsigned int* ticket, double* norm2_out, const int* __restrict__ skip) {
   extern __shared__ double s_coef[];
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
+  if (skip && *skip) return;
   for (uint32_t t = threadIdx.x; t < nvec; t += kBlock) s_coef[t] = sign * coef[t];
   __syncthreads();
   const uint64_t n2 = n >> 1, ld2 = ldv >> 1;
@@ -877,6 +881,20 @@ __global__ void __launch_bounds__(kBlock) k_tridiag_expv(uint32_t k, const doubl
   if (bad) atomicOr(status, 0x40000000);
 }
 
+// "Twice is enough" (Daniel-Gragg-Kaufman-Stewart): after one classical Gram-Schmidt pass the second is needed only if the
+// projection removed a substantial part of the vector, ||w_after||^2 < 1/2 ||w_before||^2. Decided on the device so the
+// host never waits; the second pass's kernels exit at once when *skip != 0.
+__global__ void k_reorth_decide(const double* __restrict__ norm2_before, const double* __restrict__ norm2_after, int* __restrict__ skip,
+                                unsigned int* __restrict__ second_passes, int always) {
+  const bool need = always || !(*norm2_after >= 0.5 * *norm2_before);   // also true for NaN
+  *skip = need ? 0 : 1;
+  if (need) atomicAdd(second_passes, 1u);
+}
+// norm2 = (second pass ran) ? norm2_second : unchanged
+__global__ void k_reorth_select(const int* __restrict__ skip, const double* __restrict__ norm2_second, double* __restrict__ norm2) {
+  if (!*skip) *norm2 = *norm2_second;
+}
+
 inline unsigned stream_grid(const lz_ctx* c, uint64_t work_items /* per-thread items */) {
   uint64_t want = (work_items + kBlock - 1) / kBlock;
   uint64_t cap = (uint64_t)c->sm_count * 8;
@@ -1015,22 +1033,34 @@ int lz_k_norm2(lz_ctx* c, const double* v, uint64_t len, double* out) {
   return LZ_OK;
 }
 
-int lz_k_multidot(lz_ctx* c, const double* V, uint32_t nvec, const double* w, double* h_out) {
+int lz_k_multidot(lz_ctx* c, const double* V, uint32_t nvec, const double* w, double* h_out, const int* skip) {
   unsigned g = (unsigned)c->sm_count * 4;
   uint64_t want = (c->n_loc / 2 + kBlock) / kBlock;
   if (want < g) g = (unsigned)(want ? want : 1);
   LZ_TRY(ensure_partials(c, (uint64_t)g * nvec));
-  k_multidot<<<g, kBlock, 0, c->stream>>>(V, c->ldv, nvec, w, c->n_loc, c->partials, c->ticket + 3, h_out);
+  k_multidot<<<g, kBlock, 0, c->stream>>>(V, c->ldv, nvec, w, c->n_loc, c->partials, c->ticket + 3, h_out, skip);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
 
 int lz_k_combine(lz_ctx* c, const double* V, uint32_t nvec, const double* coef, double coef_sign, const double* base, double* out,
-                 double* norm2_out) {
+                 double* norm2_out, const int* skip) {
   unsigned g = stream_grid(c, c->n_loc / 2 + 1);
   LZ_TRY(ensure_partials(c, g));
   k_combine<<<g, kBlock, nvec * sizeof(double), c->stream>>>(V, c->ldv, nvec, coef, coef_sign, base, out, c->n_loc, c->partials,
-                                                             c->ticket + 4, norm2_out);
+                                                             c->ticket + 4, norm2_out, skip);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_reorth_decide(lz_ctx* c, const double* norm2_before, const double* norm2_after, int* skip, unsigned int* second_passes) {
+  static const int always = getenv("LZ_REORTH_ALWAYS_TWICE") && atoi(getenv("LZ_REORTH_ALWAYS_TWICE")) != 0;   // test knob
+  k_reorth_decide<<<1, 1, 0, c->stream>>>(norm2_before, norm2_after, skip, second_passes, always);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+int lz_k_reorth_select(lz_ctx* c, const int* skip, const double* norm2_second, double* norm2) {
+  k_reorth_select<<<1, 1, 0, c->stream>>>(skip, norm2_second, norm2);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }

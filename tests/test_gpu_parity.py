@@ -323,3 +323,21 @@ def test_convergence_estimate_matches_actual_change(lz, orc, golden, ctx):
     assert est[8] > est[12] > est[16]
     with pytest.raises(lz.LzError):
         ctx.estimate_change(20)
+
+
+@pytest.mark.parametrize("always", ["0", "1"])
+def test_reorth_second_pass_path(always):
+    """LZ_REORTH_FULL repeats the Gram-Schmidt pass only when needed; force it every step to exercise that path too."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LZ_REORTH_ALWAYS_TWICE=always)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "reorth_twice_check.py")], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["rel"] < TOL and out["orth"] < 1e-12
+    assert out["second_passes"] == (29 if always == "1" else out["second_passes"])
+    if always == "0":
+        assert out["second_passes"] <= 29
