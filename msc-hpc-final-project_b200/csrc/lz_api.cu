@@ -39,6 +39,10 @@ const lz_nccl_api* lz_nccl() {
   return &api;
 }
 
+static void drop_graph(lz_ctx* c) {
+  if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+}
+
 namespace {
 
 int set_dev(lz_ctx* c) {
@@ -155,6 +159,7 @@ int ensure_graph_vectors(lz_ctx* c) {
   }
   free_vectors(c);
   c->ldv = ldv; c->vec_n = c->n; c->vec_nloc = c->n_loc;
+  c->epoch++;
   LZ_CUDA(cudaMalloc((void**)&c->w, ldv * 8));
   LZ_CUDA(cudaMalloc((void**)&c->ans, ldv * 8));
   LZ_CUDA(cudaMalloc((void**)&c->xstage, c->n * 8));
@@ -330,6 +335,7 @@ extern "C" int lz_destroy(lz_ctx* c) {
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_scaled) cudaEventDestroy(c->ev_scaled);
   for (int b = 0; b < LZ_MAX_COLBLK; b++) if (c->ev_chunk[b]) cudaEventDestroy(c->ev_chunk[b]);
+  drop_graph(c);
   free_vectors(c);
   lz_free_graph(c);
   cudaFree(c->scal); cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->status); cudaFree(c->flush_buf);
@@ -376,25 +382,11 @@ extern "C" int lz_set_start_vector(lz_ctx* c, const double* x_host) {
   return LZ_OK;
 }
 
-extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
-  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
-  if (k < 1) return lz_fail(LZ_ERR_ARG, "krylov dimension must be >= 1");
-  if (reorth != LZ_REORTH_NONE && reorth != LZ_REORTH_FULL) return lz_fail(LZ_ERR_ARG, "bad reorth mode %d", reorth);
-  if (!c->have_x) return lz_fail(LZ_ERR_ARG, "lz_set_start_vector must be called before lz_lanczos_run");
-  LZ_TRY(set_dev(c));
-  LZ_TRY(ensure_k(c, k));
+// Enqueues the k Lanczos steps on c->stream (also used under stream capture for the CUDA-graph path).
+static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, bool peer_scalars) {
   const uint64_t ldv = c->ldv;
   const bool dist = c->world > 1;
-  // chunk 0 of each new vector is sent by the normalisation kernel, chunk b + 1 by SpMV pass b (sliced variant only)
-  bool fused_push = c->peer_push && c->spmv_variant == LZ_SPMV_AUTO && c->ncolblk > 1;
-  // plain Lanczos on the sliced variant: alpha and ||w||^2 are reduced through peer memory too (no collective launches)
-  bool peer_scalars = c->peer_push && c->spmv_variant == LZ_SPMV_AUTO && reorth == LZ_REORTH_NONE;
-  if (const char* e = getenv("LZ_PEER_SCALARS")) peer_scalars = peer_scalars && atoi(e) != 0;
-  if (const char* e = getenv("LZ_FUSED_PUSH")) fused_push = fused_push && atoi(e) != 0;
-  c->ev_used = 0;
-  g_marks.clear();
   LZ_CUDA(cudaMemsetAsync(c->status + 2, 0, sizeof(int), c->stream));
-  LZ_CUDA(cudaEventRecord(c->ev_a, c->stream));
   if (dist) {   // q_0 into the gathered buffer (a previous run left q_{k-1} there)
     if (c->peer_push) {
       LZ_TRY(lz_k_scale_push(c, c->V, nullptr, c->V, nullptr, ++c->push_seq, fused_push ? 1u : c->ncolblk));
@@ -445,6 +437,62 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
     }
     if (!c->peer_push) LZ_TRY(allgather_chunks(c, c->xfull, true));
   }
+  return LZ_OK;
+}
+
+extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
+  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  if (k < 1) return lz_fail(LZ_ERR_ARG, "krylov dimension must be >= 1");
+  if (reorth != LZ_REORTH_NONE && reorth != LZ_REORTH_FULL) return lz_fail(LZ_ERR_ARG, "bad reorth mode %d", reorth);
+  if (!c->have_x) return lz_fail(LZ_ERR_ARG, "lz_set_start_vector must be called before lz_lanczos_run");
+  LZ_TRY(set_dev(c));
+  LZ_TRY(ensure_k(c, k));
+  // chunk 0 of each new vector is sent by the normalisation kernel, chunk b + 1 by SpMV pass b (sliced variant only)
+  bool fused_push = c->peer_push && c->spmv_variant == LZ_SPMV_AUTO && c->ncolblk > 1;
+  // plain Lanczos on the sliced variant: alpha and ||w||^2 are reduced through peer memory too (no collective launches)
+  bool peer_scalars = c->peer_push && c->spmv_variant == LZ_SPMV_AUTO && reorth == LZ_REORTH_NONE;
+  if (const char* e = getenv("LZ_PEER_SCALARS")) peer_scalars = peer_scalars && atoi(e) != 0;
+  if (const char* e = getenv("LZ_FUSED_PUSH")) fused_push = fused_push && atoi(e) != 0;
+  c->ev_used = 0;
+  g_marks.clear();
+  // Small problems are launch-bound (3 launches of ~10-80 us per step): replay the whole k-step loop as one CUDA graph.
+  // Single GPU only (the peer exchange bakes per-run sequence numbers into kernel arguments), and not while profiling.
+  bool use_graph = c->world == 1 && !c->profiling && c->n_loc <= (4u << 20);
+  if (const char* e = getenv("LZ_CUDA_GRAPH")) use_graph = c->world == 1 && !c->profiling && atoi(e) != 0;
+  LZ_CUDA(cudaEventRecord(c->ev_a, c->stream));
+  bool done = false;
+  if (use_graph) {
+    const bool hit = c->graph_exec && c->graph_k == k && c->graph_reorth == reorth && c->graph_variant == c->spmv_variant &&
+                     c->graph_V == c->V && c->graph_epoch == c->epoch;
+    if (!hit) {
+      drop_graph(c);
+      // no allocation may happen inside the capture: size the reduction scratch for the largest grid of the loop
+      LZ_TRY(lz_k_reserve_partials(c, (uint64_t)c->sm_count * 8 * (reorth ? (k > 8 ? k : 8) : 8)));
+      const uint32_t launches0 = c->launches;
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int rc = enqueue_steps(c, k, reorth, fused_push, peer_scalars);
+        const cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+        if (rc == LZ_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&c->graph_exec, g, 0) == cudaSuccess) {
+          c->graph_k = k; c->graph_reorth = reorth; c->graph_variant = c->spmv_variant; c->graph_V = c->V; c->graph_epoch = c->epoch;
+          c->graph_launches = c->launches - launches0;
+        } else {
+          c->graph_exec = nullptr;
+        }
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        c->launches = launches0;
+      }
+    }
+    if (c->graph_exec && cudaGraphLaunch(c->graph_exec, c->stream) == cudaSuccess) {
+      c->launches += c->graph_launches;
+      done = true;
+    } else {
+      cudaGetLastError();
+      drop_graph(c);
+    }
+  }
+  if (!done) LZ_TRY(enqueue_steps(c, k, reorth, fused_push, peer_scalars));
   LZ_CUDA(cudaEventRecord(c->ev_b, c->stream));
   c->k_done = k;
   c->reorth_done = reorth;

@@ -143,6 +143,13 @@ struct lz_ctx {
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
 
+  // ---- CUDA graph of the k-step loop (single GPU, small problems) ----------------------------------------------
+  cudaGraphExec_t graph_exec = nullptr;
+  uint32_t graph_k = 0, graph_launches = 0;
+  int graph_reorth = 0, graph_variant = 0;
+  double* graph_V = nullptr;
+  uint64_t graph_epoch = 0, epoch = 0;   // epoch: bumped whenever the graph data or the vectors are re-created
+
   // ---- measurement ------------------------------------------------------------------------------------------------
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -185,3 +192,4 @@ int lz_k_tridiag_expv_into(lz_ctx* c, uint32_t k, double* eigvals, double* eigve
 int lz_k_permute_in(lz_ctx* c, const double* x_orig, const double* norm2, uint64_t first, uint64_t count, double* dst);
 int lz_k_permute_out(lz_ctx* c, const double* y_new_full, double* y_orig);
 int lz_k_fill(lz_ctx* c, double* p, uint64_t n, double value);
+int lz_k_reserve_partials(lz_ctx* c, uint64_t count);

@@ -276,6 +276,7 @@ static void make_plans(const uint32_t* bounds, uint32_t n_loc, uint32_t nblk, co
 // Takes ownership of ro_d / ci_d (original-order CSR on the device).
 int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, uint32_t* ci_d) {
   lz_free_graph(c);
+  c->epoch++;   // any cached CUDA graph of the step loop refers to the old matrix
   c->orig_ro = ro_d; c->orig_ci = ci_d;
   c->n = n; c->nnz = nnz;
   const uint32_t world = (uint32_t)c->world, rank = (uint32_t)c->rank;

@@ -1108,3 +1108,5 @@ int lz_k_fill(lz_ctx* c, double* p, uint64_t n, double value) {
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
+
+int lz_k_reserve_partials(lz_ctx* c, uint64_t count) { return ensure_partials(c, count); }
