@@ -262,8 +262,11 @@ extern "C" int lz_device_count(int* count_out) {
   return LZ_OK;
 }
 
+static int create_body(lz_ctx* c, int device, int rank, int world, const void* uid);
+
 static int create_common(int device, int rank, int world, const void* uid, lz_ctx** out) {
   if (!out) return lz_fail(LZ_ERR_ARG, "null ctx_out");
+  *out = nullptr;
   if (world < 1 || rank < 0 || rank >= world) return lz_fail(LZ_ERR_ARG, "bad rank %d / world %d", rank, world);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -273,6 +276,18 @@ static int create_common(int device, int rank, int world, const void* uid, lz_ct
   LZ_CUDA(cudaSetDevice(device));
   lz_ctx* c = new (std::nothrow) lz_ctx();
   if (!c) return lz_fail(LZ_ERR_ALLOC, "out of host memory");
+  const int rc = create_body(c, device, rank, world, uid);
+  if (rc != LZ_OK) {          // keep the message of the failure, release whatever was created
+    char msg[512];
+    snprintf(msg, sizeof(msg), "%s", lz_last_error());
+    lz_destroy(c);
+    return lz_fail(rc, "%s", msg);
+  }
+  *out = c;
+  return LZ_OK;
+}
+
+static int create_body(lz_ctx* c, int device, int rank, int world, const void* uid) {
   c->device = device; c->rank = rank; c->world = world;
   cudaDeviceProp prop;
   LZ_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -305,7 +320,6 @@ static int create_common(int device, int rank, int world, const void* uid, lz_ct
     LZ_CUDA(cudaEventCreateWithFlags(&c->ev_scaled, cudaEventDisableTiming));
     for (int b = 0; b < LZ_MAX_COLBLK; b++) LZ_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[b], cudaEventDisableTiming));
   }
-  *out = c;
   return LZ_OK;
 }
 
@@ -327,7 +341,7 @@ extern "C" int lz_create_dist(int device, int rank, int world, const void* uid, 
 extern "C" int lz_destroy(lz_ctx* c) {
   if (!c) return LZ_OK;
   cudaSetDevice(c->device);
-  const bool healthy = cudaStreamSynchronize(c->stream) == cudaSuccess;
+  const bool healthy = !c->stream || cudaStreamSynchronize(c->stream) == cudaSuccess;
   // after a device fault a collective may never complete on the peers: abort instead of the (blocking) destroy
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c->comm_ag && lz_nccl()) { if (healthy) lz_nccl()->CommDestroy(c->comm_ag); else lz_nccl()->CommAbort(c->comm_ag); }
@@ -340,9 +354,10 @@ extern "C" int lz_destroy(lz_ctx* c) {
   lz_free_graph(c);
   cudaFree(c->scal); cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->status); cudaFree(c->flush_buf);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
-  cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_e0); cudaEventDestroy(c->ev_e1);
-  cudaEventDestroy(c->ev_m0); cudaEventDestroy(c->ev_m1); cudaEventDestroy(c->ev_t0); cudaEventDestroy(c->ev_t1);
-  cudaStreamDestroy(c->stream);
+  for (cudaEvent_t e : {c->ev_a, c->ev_b, c->ev_e0, c->ev_e1, c->ev_m0, c->ev_m1, c->ev_t0, c->ev_t1})
+    if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  cudaGetLastError();
   delete c;
   return LZ_OK;
 }
