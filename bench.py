@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=int, default=None, help="override the R-MAT scale (debug)")
     ap.add_argument("--k", type=int, default=None)
-    ap.add_argument("--n", type=int, default=None, help="override n of the ER / banded workloads (debug)")
+    ap.add_argument("--vertices", dest="n", type=int, default=None, help="override n of the ER / banded workloads (debug)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reorth-detail", action="store_true")

@@ -47,6 +47,17 @@ def main():
         assert np.array_equal(ctx.spmv_host(x), orc.spmv(ro, ci, x)), name
         q3 = ctx.get_basis(min(3, k - 1))
         assert abs(q3 @ q3 - 1) < 1e-12
+    # natural vertex order (contiguous row blocks per rank), forced: band-like and skewed graph
+    os.environ["LZ_ORDER"] = "n"
+    for name in ("band_n4096_k40", "rmat_s12_k30"):
+        gl = np.load(os.path.join(gdir, name + ".npz"))
+        ro, ci, k, n = gl["row_offset"], gl["col_idx"], int(gl["k"]), int(gl["n"])
+        ctx.csr_upload(ro, ci)
+        y = ctx.expv_host(None, k)
+        assert rel2(y, gl["ans"]) < 1e-9, ("natural", name, rel2(y, gl["ans"]))
+        x = np.random.default_rng(6).integers(-1000, 1000, n).astype(np.float64)
+        assert np.array_equal(ctx.spmv_host(x), orc.spmv(ro, ci, x)), name
+    del os.environ["LZ_ORDER"]
     # generated graph, compared with the CPU oracle
     spec = lz.GraphSpec.rmat(16, 8, 1)
     ctx.graph_generate(spec)
