@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as graft  # noqa: E402
 
 METRIC, UNIT = "lanczos_iterations_per_sec", "iterations/s"
+GATHER_CEILING = 275.0   # 1e9 random 8-byte gathers per second, measured on this pool's B200 (one line lookup per clock per SM)
 
 # BASELINE.json configs. `k`/`reorth` are the config's; the default bench line uses plain Lanczos
 # (what the reference computes and what the roofline formula 4*nnz + 68*n describes) and reports the config's
@@ -282,7 +283,11 @@ def main():
     spmv_gbs = b_spmv / (tm.spmv_ms_avg * 1e-3) / 1e9 if tm.spmv_ms_avg else None
     roofline = {"bound": "hbm", "kernel": "k_spmv_dot", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
                 "frac": (spmv_gbs / peak) if spmv_gbs else None, "traffic": ncu_traffic(args.workload),
-                "algorithmic_bytes_per_launch": b_spmv, "peak_source": peak_src}
+                "algorithmic_bytes_per_launch": b_spmv, "peak_source": peak_src,
+                # what actually binds this kernel on a random graph: the SM load path's line-lookup rate
+                "gather": {"achieved_ggathers_s": gi.nnz_local / (tm.spmv_ms_avg * 1e-3) / 1e9 if tm.spmv_ms_avg else None,
+                           "ceiling_ggathers_s": GATHER_CEILING, "frac": (gi.nnz_local / (tm.spmv_ms_avg * 1e-3) / 1e9 / GATHER_CEILING)
+                           if tm.spmv_ms_avg else None, "ceiling_source": "profiles/microbench/gather_bench_r01.txt (L2-resident random 8-B gathers)"}}
     b_iter = 4.0 * gi.nnz_local + 68.0 * gi.n_local
     detail["iteration_roofline_iters_per_s"] = peak * 1e9 / b_iter
     detail["iteration_frac_of_roofline"] = (k / (tm.lanczos_ms * 1e-3)) / (peak * 1e9 / b_iter) if tm.lanczos_ms else None
@@ -306,16 +311,25 @@ def main():
     # end to end through the reference-facing call with HOST buffers (pinned), H2D of x and D2H of the answer inside
     x_host = torch.ones(n, dtype=torch.float64).pin_memory().numpy()
     y_host = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+    want = rank == 0                               # the caller (rank 0) holds x and receives e^A x; the other ranks only compute
+
+    def e2e_call():
+        if world > 1:
+            ctx.expv_host_root(x_host, k, out=y_host, root=0)    # one PCIe upload, NVLink broadcast, one download
+        else:
+            ctx.expv_host(x_host, k, out=y_host)
     for _ in range(2):
-        ctx.expv_host(x_host, k, out=y_host)
+        e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.expv_host(x_host, k, out=y_host)       # synchronous: returns after the D2H copy of the answer
+        e2e_call()                                 # synchronous: returns after the D2H copy of the answer
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": k * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
-           "ms_per_step": 1e3 * e2e_s / args.steps, "call": "lz_expv_host (pinned host x -> pinned host e^A x)"}
-    finite = bool(np.isfinite(y_host).all())
+           "ms_per_step": 1e3 * e2e_s / args.steps,
+           "call": "lz_expv_host (pinned host x -> pinned host e^A x)" if world == 1 else
+                   "lz_expv_host_root (rank 0: pinned host x -> NVLink broadcast -> ... -> pinned host e^A x)"}
+    finite = bool(np.isfinite(y_host).all()) if want else True
 
     # CPU baseline: the reference's own serial Lanczos on the same graph, bounded sample, rank 0, N == 1 only
     cpu = None

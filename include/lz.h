@@ -112,6 +112,8 @@ int lz_csr_download(lz_ctx* ctx, uint32_t* row_offset_out, uint32_t* col_idx_out
 
 /* x (n doubles, original order; NULL = all ones as in main.cu:79) -> device, computes ||x|| (cu_lanczos.h:18-24,63). */
 int lz_set_start_vector(lz_ctx* ctx, const double* x_host);
+/* Multi-GPU: only rank `root` reads x_host (one PCIe upload); the other ranks receive the vector over NVLink. Collective. */
+int lz_set_start_vector_root(lz_ctx* ctx, const double* x_host, int root);
 /* k Lanczos steps, basis V kept resident on the device (parallel-mult-on-card/lib/cu_lanczos.cu:39,57), alpha/beta in
  * device memory. Enqueue only. Replaces lanczosDecomp<T>::cu_decompose (parallel-final/lib/cu_lanczos.cu:97-128). */
 int lz_lanczos_run(lz_ctx* ctx, uint32_t k, int reorth);
@@ -130,11 +132,14 @@ int lz_estimate_change(lz_ctx* ctx, uint32_t k_prev, double* rel_out);
 /* ans = V * c as a tall-skinny GEMV on the device. Replaces multOut's cblas_dgemv (multiplyOut.cu:43-47) and
  * cu_multOut's cublasDgemv (parallel-mult-on-card/lib/cu_multiplyOut.cu:66-72). Enqueue only. */
 int lz_multout(lz_ctx* ctx);
-/* ans (n doubles, original order) to the host on every rank (cublasGetVector, cu_multiplyOut.cu:77). Synchronises. */
+/* ans (n doubles, original order) to the host (cublasGetVector, cu_multiplyOut.cu:77). Synchronises. With world > 1 the call
+ * is collective; a rank that does not need the vector may pass NULL (it still takes part in the gather). */
 int lz_get_ans(lz_ctx* ctx, double* ans_host);
 /* Whole pipeline with HOST buffers, what lanczosDecomp<double>(A,k,x,true) + eigenDecomp + multOut do in main.cu:115-127:
  * H2D x, k steps, eigensolve, multOut, D2H ans. */
 int lz_expv_host(lz_ctx* ctx, const double* x_host, uint32_t k, int reorth, double* ans_host);
+/* Same with one caller: only rank `root` passes x_host and receives ans_host (ignored on the other ranks). Collective. */
+int lz_expv_host_root(lz_ctx* ctx, const double* x_host, uint32_t k, int reorth, double* ans_host, int root);
 
 /* ---- test hooks / measurement --------------------------------------------------------------------------------------- */
 /* y = A x with host vectors in original order (all ranks get the full y). Parity hook against spMV, SPMV.cc:19-28. */

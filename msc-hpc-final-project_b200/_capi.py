@@ -96,6 +96,8 @@ _sig("lz_estimate_change", _ctx, C.c_uint32, _P(C.c_double))
 _sig("lz_multout", _ctx)
 _sig("lz_get_ans", _ctx, _f64p)
 _sig("lz_expv_host", _ctx, _f64p, C.c_uint32, C.c_int, _f64p)
+_sig("lz_expv_host_root", _ctx, _f64p, C.c_uint32, C.c_int, _f64p, C.c_int)
+_sig("lz_set_start_vector_root", _ctx, _f64p, C.c_int)
 _sig("lz_spmv_host", _ctx, _f64p, _f64p)
 _sig("lz_get_basis", _ctx, C.c_uint32, _f64p)
 _sig("lz_set_spmv_variant", _ctx, C.c_int)
@@ -275,11 +277,27 @@ class Context:
         _check(lib.lz_get_ans(self._h, _f64(y)))
         return y
 
-    def expv_host(self, x, k, reorth=REORTH_NONE, out=None):
+    def expv_host(self, x, k, reorth=REORTH_NONE, out=None, want_result=True):
+        """want_result=False (world > 1 only): this rank takes part but does not copy e^A x to its host."""
+        n = self.graph_info().n
+        y = None
+        if want_result:
+            y = np.empty(n) if out is None else out
+        xp = None if x is None else _f64(np.ascontiguousarray(x, np.float64))
+        _check(lib.lz_expv_host(self._h, xp, k, reorth, _f64(y) if want_result else None))
+        self._k = k
+        return y
+
+    def expv_host_root(self, x, k, reorth=REORTH_NONE, out=None, root=0):
+        """One caller: only `root` passes x and receives e^A x (returns None elsewhere)."""
+        if self.rank != root:
+            _check(lib.lz_expv_host_root(self._h, None, k, reorth, None, root))
+            self._k = k
+            return None
         n = self.graph_info().n
         y = np.empty(n) if out is None else out
-        xp = None if x is None else _f64(np.ascontiguousarray(x, np.float64))
-        _check(lib.lz_expv_host(self._h, xp, k, reorth, _f64(y)))
+        x = np.ascontiguousarray(x, np.float64)
+        _check(lib.lz_expv_host_root(self._h, _f64(x), k, reorth, _f64(y), root))
         self._k = k
         return y
 

@@ -32,6 +32,7 @@ const lz_nccl_api* lz_nccl() {
   api.CommSplit = (decltype(api.CommSplit))dlsym(h, "ncclCommSplit");   // optional
   api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
   api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+  api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
   api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
   api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
   if (!ok) { state = -1; lz_fail(LZ_ERR_NCCL, "libnccl.so.2 lacks a required symbol"); return nullptr; }
@@ -377,11 +378,20 @@ extern "C" int lz_set_spmv_variant(lz_ctx* c, int variant) {
 
 // x -> device, ||x||^2 -> scal[2], q_0 = x/||x|| -> V[0] (and the gathered buffer when world > 1).
 // Replaces cu_lanczos.cu:30-34 (host normalisation) + :88 (H2D of q_0).
-extern "C" int lz_set_start_vector(lz_ctx* c, const double* x_host) {
+// root < 0: every rank passes the vector itself (or NULL = ones). root >= 0: only `root` reads x_host; the other ranks
+// receive it over NVLink (one PCIe upload instead of `world` concurrent ones).
+static int set_start_vector_impl(lz_ctx* c, const double* x_host, int root) {
   if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  if (root >= c->world) return lz_fail(LZ_ERR_ARG, "root %d out of range", root);
   LZ_TRY(set_dev(c));
   LZ_TRY(ensure_k(c, c->k_cap ? c->k_cap : 2));
-  if (x_host) {
+  if (root >= 0 && c->world > 1) {
+    if (c->rank == root) {
+      if (!x_host) return lz_fail(LZ_ERR_ARG, "the root rank must pass the start vector");
+      LZ_CUDA(cudaMemcpyAsync(c->xstage, x_host, c->n * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    LZ_NCCL(lz_nccl()->Broadcast(c->xstage, c->xstage, c->n, ncclDouble, root, c->comm, c->stream));
+  } else if (x_host) {
     LZ_CUDA(cudaMemcpyAsync(c->xstage, x_host, c->n * 8, cudaMemcpyHostToDevice, c->stream));
   } else {
     LZ_TRY(lz_k_fill(c, c->xstage, c->n, 1.0));   // all ones, as every reference driver uses (main.cu:79)
@@ -453,6 +463,12 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
     if (!c->peer_push) LZ_TRY(allgather_chunks(c, c->xfull, true));
   }
   return LZ_OK;
+}
+
+extern "C" int lz_set_start_vector(lz_ctx* c, const double* x_host) { return set_start_vector_impl(c, x_host, -1); }
+extern "C" int lz_set_start_vector_root(lz_ctx* c, const double* x_host, int root) {
+  if (root < 0) return lz_fail(LZ_ERR_ARG, "root must be >= 0");
+  return set_start_vector_impl(c, x_host, root);
 }
 
 extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
@@ -615,21 +631,32 @@ static int gather_to_host(lz_ctx* c, const double* local, double* host_out) {
     LZ_TRY(allgather_chunks(c, c->gfull, false));
     full = c->gfull;
   }
-  LZ_TRY(lz_k_permute_out(c, full, c->xstage));
-  LZ_CUDA(cudaMemcpyAsync(host_out, c->xstage, c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (host_out) {   // ranks that do not need the vector on the host still take part in the gather above
+    LZ_TRY(lz_k_permute_out(c, full, c->xstage));
+    LZ_CUDA(cudaMemcpyAsync(host_out, c->xstage, c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
   LZ_CUDA(cudaStreamSynchronize(c->stream));
   return LZ_OK;
 }
 
 extern "C" int lz_get_ans(lz_ctx* c, double* ans_host) {
-  if (!c || !ans_host) return lz_fail(LZ_ERR_ARG, "null argument");
+  if (!c || (!ans_host && c->world == 1)) return lz_fail(LZ_ERR_ARG, "null argument");
   if (!c->have_ans) return lz_fail(LZ_ERR_ARG, "lz_multout must be called before lz_get_ans");
   LZ_TRY(set_dev(c));
   return gather_to_host(c, c->ans, ans_host);
 }
 
+static int expv_impl(lz_ctx* c, const double* x_host, uint32_t k, int reorth, double* ans_host, int root);
 extern "C" int lz_expv_host(lz_ctx* c, const double* x_host, uint32_t k, int reorth, double* ans_host) {
-  LZ_TRY(lz_set_start_vector(c, x_host));
+  return expv_impl(c, x_host, k, reorth, ans_host, -1);
+}
+// One caller holds x and wants e^A x: only rank `root` touches host memory (x_host / ans_host are ignored elsewhere).
+extern "C" int lz_expv_host_root(lz_ctx* c, const double* x_host, uint32_t k, int reorth, double* ans_host, int root) {
+  if (!c || root < 0 || root >= c->world) return lz_fail(LZ_ERR_ARG, "bad root");
+  return expv_impl(c, c->rank == root ? x_host : nullptr, k, reorth, c->rank == root ? ans_host : nullptr, root);
+}
+static int expv_impl(lz_ctx* c, const double* x_host, uint32_t k, int reorth, double* ans_host, int root) {
+  LZ_TRY(set_start_vector_impl(c, x_host, root));
   LZ_TRY(lz_lanczos_run(c, k, reorth));
   LZ_TRY(lz_tridiag_expv(c));
   LZ_TRY(lz_multout(c));

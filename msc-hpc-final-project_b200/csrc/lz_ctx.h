@@ -22,6 +22,7 @@ struct lz_nccl_api {
   ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*);   // may be null (NCCL < 2.18)
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   const char* (*GetErrorString)(ncclResult_t);
   ncclResult_t (*GetVersion)(int*);
 };

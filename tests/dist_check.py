@@ -66,6 +66,13 @@ def main():
     y = ctx.expv_host(None, 30)
     ref, _, _ = orc.expv(ro, ci, 30, np.ones(n))
     assert rel2(y, ref) < 1e-9 and np.array_equal(orc.top_k(y), orc.top_k(ref))
+    # single-caller entry point: only rank 0 passes x and receives the answer
+    xr = np.random.default_rng(9).random(n)
+    yr_all = ctx.expv_host(xr, 30)
+    yr_root = ctx.expv_host_root(xr if rank == 0 else None, 30, root=0)
+    assert (yr_root is None) == (rank != 0)
+    if rank == 0:
+        assert np.array_equal(yr_root, yr_all)
     # every rank holds the same answer bit for bit
     ys = [None] * world
     dist.all_gather_object(ys, y.tobytes())
