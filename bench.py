@@ -277,11 +277,16 @@ def main():
               "lanczos_only_iters_per_s": k / (tm.lanczos_ms * 1e-3) if tm.lanczos_ms else None,
               "graph_build_s": t_graph, "max_degree": gi.max_degree, "empty_rows": gi.empty_rows}
 
-    # roofline of the dominant kernel (k_spmv_dot): algorithmic bytes 4*nnz + 20*n per launch, per GPU
+    # roofline of the dominant kernel (the SpMV: k_spmv_sell by default, k_spmv_dot for the CSR variants): algorithmic bytes 4*nnz + 20*n per launch, per GPU
     peak, peak_src = measured_peak()
-    b_spmv = 4.0 * gi.nnz_local + 4.0 * gi.n_local + 8.0 * n + 8.0 * gi.n_local   # == 4 nnz + 20 n at world == 1
+    # x is "compulsory once": every entry this rank's rows reference = its own slice + the referenced remote entries (all of x
+    # for R-MAT; a halo plus chords for band-like graphs, where the exchange reports the fraction)
+    xmode_, xfrac_ = ctx.exchange_info()
+    x_ref = n if xmode_ in (0, 1) else gi.n_local * (1.0 + xfrac_ * (world - 1))
+    b_spmv = 4.0 * gi.nnz_local + 4.0 * gi.n_local + 8.0 * min(x_ref, n) + 8.0 * gi.n_local   # == 4 nnz + 20 n at world == 1
     spmv_gbs = b_spmv / (tm.spmv_ms_avg * 1e-3) / 1e9 if tm.spmv_ms_avg else None
-    roofline = {"bound": "hbm", "kernel": "k_spmv_dot", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
+    spmv_kernel = "k_spmv_sell" if os.environ.get("LZ_SPMV_VARIANT", "0") in ("", "0") else "k_spmv_dot"
+    roofline = {"bound": "hbm", "kernel": spmv_kernel, "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
                 "frac": (spmv_gbs / peak) if spmv_gbs else None, "traffic": ncu_traffic(args.workload),
                 "algorithmic_bytes_per_launch": b_spmv, "peak_source": peak_src,
                 # what actually binds this kernel on a random graph: the SM load path's line-lookup rate
@@ -345,6 +350,9 @@ def main():
         cpu = {"value": vals[0], "unit": UNIT, "cores": 1, "kind": kind,
                "sample": f"{m} Lanczos steps of {w['name']} (reference lanczosDecomp<double>, cuda=false, single thread), {secs[0]:.1f} s",
                "host_cores_available": os.cpu_count()}
+    xmode, xfrac = ctx.exchange_info()
+    exchange = {0: "none (one GPU)", 1: "ncclAllGather", 2: "peer stores over NVLink, whole vector",
+                3: "peer stores over NVLink, referenced entries only (%.3g of the vector)" % xfrac}[xmode]
     ctx.close()
 
     if rank == 0:
@@ -354,7 +362,7 @@ def main():
                 "config": {"workload": w["name"], "n": n, "nnz": nnz, "k": k, "reorth": "none", "x": "ones",
                            "l2_policy": "inputs larger than L2 (CSR %.2f GB + basis %.2f GB per GPU)" % (
                                (4.0 * gi.nnz_local + 4 * gi.n_local) / 1e9, 8.0 * gi.n_local * k / 1e9),
-                           "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                           "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU", "exchange": exchange,
                            "launch": "CUDA graph replay of the k-step loop" if graph_replay else "stream launches"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "result_finite": finite, "detail": detail}

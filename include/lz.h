@@ -153,6 +153,17 @@ int lz_get_basis(lz_ctx* ctx, uint32_t j, double* q_host);
 #define LZ_SPMV_WARP 2     /* CSR, one warp per row for every row                                                     */
 int lz_set_spmv_variant(lz_ctx* ctx, int variant);
 
+/* How the Krylov vector travels between the ranks of a multi-GPU context (valid once a start vector has been set):
+ * in full through ncclAllGather, in full by peer stores over NVLink, or — when each rank's rows reference only a small part
+ * of the other ranks' entries (band-like graphs: a halo plus chords) — only the referenced entries by peer stores.
+ * need_frac = referenced remote entries / entries a full exchange would send, over all ranks. Generalises the whole-half-
+ * vector cudaMemcpyPeer of parallel-two-cards/lib/cu_lanczos.cu:116-165. */
+#define LZ_EXCHANGE_NONE 0         /* one GPU */
+#define LZ_EXCHANGE_NCCL 1
+#define LZ_EXCHANGE_PEER_DENSE 2
+#define LZ_EXCHANGE_PEER_SPARSE 3
+int lz_exchange_info(lz_ctx* ctx, int* mode_out, double* need_frac_out);
+
 typedef struct lz_timings {
   float lanczos_ms;     /* device time of the last lz_lanczos_run (cudaEvent pair on the ctx stream) */
   float tridiag_ms;     /* last lz_tridiag_expv                                                      */

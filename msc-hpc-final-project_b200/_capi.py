@@ -17,6 +17,7 @@ lib = C.CDLL(lib_path)
 
 GRAPH_ER, GRAPH_RMAT, GRAPH_BAND = 1, 2, 3
 REORTH_NONE, REORTH_FULL = 0, 1
+EXCHANGE_NONE, EXCHANGE_NCCL, EXCHANGE_PEER_DENSE, EXCHANGE_PEER_SPARSE = 0, 1, 2, 3
 SPMV_AUTO, SPMV_VECTOR, SPMV_WARP = 0, 1, 2
 NCCL_UID_BYTES = 128
 
@@ -102,6 +103,7 @@ _sig("lz_spmv_host", _ctx, _f64p, _f64p)
 _sig("lz_get_basis", _ctx, C.c_uint32, _f64p)
 _sig("lz_set_spmv_variant", _ctx, C.c_int)
 _sig("lz_set_profiling", _ctx, C.c_int)
+_sig("lz_exchange_info", _ctx, _P(C.c_int), _P(C.c_double))
 _sig("lz_timings_get", _ctx, _P(Timings))
 _sig("lz_timer_start", _ctx)
 _sig("lz_timer_stop", _ctx, _P(C.c_float))
@@ -318,6 +320,12 @@ class Context:
 
     def set_profiling(self, on):
         _check(lib.lz_set_profiling(self._h, int(on)))
+
+    def exchange_info(self):
+        """(mode, need_frac): mode is one of EXCHANGE_NONE / _NCCL / _PEER_DENSE / _PEER_SPARSE."""
+        mode, frac = C.c_int(0), C.c_double(0)
+        _check(lib.lz_exchange_info(self._h, C.byref(mode), C.byref(frac)))
+        return mode.value, frac.value
 
     def timings(self):
         t = Timings()

@@ -60,6 +60,8 @@ void close_peers(lz_ctx* c) {
     c->peer_xfull[r] = nullptr; c->peer_flags[r] = nullptr; c->peer_ipc[r] = false;
   }
   c->peer_push = false;
+  cudaFree(c->push_list); c->push_list = nullptr;
+  c->sparse_push = false;
 }
 
 void free_vectors(lz_ctx* c) {
@@ -143,14 +145,18 @@ int setup_peers(lz_ctx* c) {
   cudaFree(dbuf);
   if (okd < 0.5) { close_peers(c); return LZ_OK; }
   c->peer_push = true;
-  return LZ_OK;
+  return lz_build_push_lists(c);
 }
 
 // Vectors that depend only on the graph size.
 int ensure_graph_vectors(lz_ctx* c) {
   if (!c->row_ptr) return lz_fail(LZ_ERR_ARG, "no graph loaded (call lz_csr_upload or lz_graph_generate first)");
   const uint64_t ldv = (c->n_loc + 31) & ~31ull;
-  if (c->w && c->ldv == ldv && c->vec_n == c->n && c->vec_nloc == c->n_loc) return LZ_OK;
+  if (c->w && c->ldv == ldv && c->vec_n == c->n && c->vec_nloc == c->n_loc) {
+    // same shape, possibly another graph: the exchange lists follow the graph, not the shape
+    if (c->world > 1 && c->peer_push && c->push_graph_id != c->graph_id) LZ_TRY(lz_build_push_lists(c));
+    return LZ_OK;
+  }
   if (c->world > 1 && c->xfull) {
     // peers may still map this rank's buffers: everybody unmaps first, then (after a barrier) everybody frees
     close_peers(c);
@@ -425,7 +431,10 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
     {  // w = A q_j ; alpha_j = w . q_j                                   (cu_lanczos.cu:101-105)
       Scope s(c, 0);
       const bool last = j + 1 == k;    // the last alpha is read by nobody on the device: reduce it with NCCL into alpha[k-1]
-      LZ_TRY(lz_k_spmv_dot(c, dist ? c->xfull : qj, qj, c->w, c->alpha + j, c->peer_push ? c->push_seq : 0ull, fused_push ? qj : nullptr,
+      // with a single chunk this rank's slots of the gathered vector are contiguous and hold the same bits as q_j: read the
+      // alpha operand from there, so it shares cache lines with the gathers instead of streaming a second copy from HBM
+      const double* q_dot = (dist && c->ncolblk == 1) ? c->xfull + (uint64_t)c->rank * c->chunk_rows : qj;
+      LZ_TRY(lz_k_spmv_dot(c, dist ? c->xfull : qj, q_dot, c->w, c->alpha + j, c->peer_push ? c->push_seq : 0ull, fused_push ? qj : nullptr,
                            (peer_scalars && !last) ? ++c->red_seq : 0ull));
     }
     if (!peer_scalars || j + 1 == k) LZ_TRY(allreduce_sum(c, c->alpha + j, 1));
@@ -479,7 +488,7 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
   LZ_TRY(set_dev(c));
   LZ_TRY(ensure_k(c, k));
   // chunk 0 of each new vector is sent by the normalisation kernel, chunk b + 1 by SpMV pass b (sliced variant only)
-  bool fused_push = c->peer_push && c->spmv_variant == LZ_SPMV_AUTO && c->ncolblk > 1;
+  bool fused_push = c->peer_push && !c->sparse_push && c->spmv_variant == LZ_SPMV_AUTO && c->ncolblk > 1;
   // plain Lanczos on the sliced variant: alpha and ||w||^2 are reduced through peer memory too (no collective launches)
   bool peer_scalars = c->peer_push && c->spmv_variant == LZ_SPMV_AUTO && reorth == LZ_REORTH_NONE;
   if (const char* e = getenv("LZ_PEER_SCALARS")) peer_scalars = peer_scalars && atoi(e) != 0;
@@ -699,6 +708,14 @@ extern "C" int lz_get_basis(lz_ctx* c, uint32_t j, double* q_host) {
 extern "C" int lz_set_profiling(lz_ctx* c, int on) {
   if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
   c->profiling = on != 0;
+  return LZ_OK;
+}
+
+extern "C" int lz_exchange_info(lz_ctx* c, int* mode_out, double* need_frac_out) {
+  if (!c || !mode_out) return lz_fail(LZ_ERR_ARG, "null argument");
+  if (c->world > 1 && !c->w) return lz_fail(LZ_ERR_ARG, "the exchange is set up by the first lz_set_start_vector / lz_expv_host");
+  *mode_out = c->world == 1 ? LZ_EXCHANGE_NONE : !c->peer_push ? LZ_EXCHANGE_NCCL : c->sparse_push ? LZ_EXCHANGE_PEER_SPARSE : LZ_EXCHANGE_PEER_DENSE;
+  if (need_frac_out) *need_frac_out = (c->world > 1 && c->peer_push) ? c->push_need_frac : 1.0;
   return LZ_OK;
 }
 

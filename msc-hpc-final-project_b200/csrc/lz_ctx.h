@@ -78,7 +78,14 @@ struct lz_ctx {
   unsigned int* push_ticket = nullptr;                // device, [LZ_MAX_COLBLK]
   unsigned long long push_seq = 0;                    // sequence number of the last push (same on every rank)
   unsigned long long red_seq = 0;                     // sequence number of the last peer scalar reduction
-  double* gfull = nullptr;                            // device, [n_loc * world], scratch for the host-facing gathers   // ev_chunk[] were recorded for the vector the next SpMV gathers from
+  double* gfull = nullptr;                            // device, [n_loc * world], scratch for the host-facing gathers
+  // Needed-columns exchange: per peer, the ascending list of this rank's rows that the peer's rows reference. Used instead of
+  // the dense push when the lists are short (lz_build_push_lists, lz_graph.cu).
+  bool sparse_push = false;
+  uint32_t* push_list = nullptr;                      // device, lists of all peers back to back
+  uint32_t push_off[LZ_MAX_WORLD + 1] = {};           // list of peer r = push_list[push_off[r] .. push_off[r + 1])
+  uint64_t graph_id = 0, push_graph_id = 0;           // graph the lists were built for (rebuilt when a new graph has the same shape)
+  double push_need_frac = 1.0;                        // referenced remote entries / dense exchange volume (global)
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;      // lz_lanczos_run
   cudaEvent_t ev_e0 = nullptr, ev_e1 = nullptr;    // lz_tridiag_expv
   cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;    // lz_multout
@@ -162,6 +169,7 @@ struct lz_ctx {
 // lz_graph.cu
 int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, uint32_t* ci_d);  // takes ownership of ro_d / ci_d
 void lz_free_graph(lz_ctx* c);
+int lz_build_push_lists(lz_ctx* c);   // collective; call after the peers are mapped
 
 // lz_kernels.cu — all launches are asynchronous on c->stream
 int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out /* device scalar or null */,

@@ -218,6 +218,37 @@ __global__ void k_sell_fill(const uint32_t* const* __restrict__ seg, const uint3
   }
 }
 
+
+// ---- needed-columns exchange (multi-GPU) -------------------------------------------------------------------------------
+// bitmap[c >> 5] bit (c & 31) = "some local row references column c" (new numbering, over the padded length)
+__global__ void k_mark_cols(const uint32_t* __restrict__ col, uint64_t m, uint32_t* __restrict__ bitmap) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = col[i], bit = 1u << (c & 31);
+    if (!(bitmap[c >> 5] & bit)) atomicOr(bitmap + (c >> 5), bit);
+  }
+}
+// Does peer `r` (bitmap bm_r) reference local row l of rank `rank`?  Chunk-major numbering as in k_relabel.
+struct NeedPred {
+  const uint32_t* bm;
+  uint64_t cl;
+  uint32_t world, rank;
+  __host__ __device__ bool operator()(uint32_t l) const {
+    const uint64_t c = l / cl, g = c * (world * cl) + (uint64_t)rank * cl + (l - c * cl);
+    return (bm[g >> 5] >> (g & 31)) & 1u;
+  }
+};
+// counts[r] = number of local rows referenced by peer r   (grid.y = world)
+__global__ void k_count_need(const uint32_t* __restrict__ bm_all, uint64_t words, uint64_t n_loc, uint64_t cl, uint32_t world, uint32_t rank,
+                             unsigned long long* __restrict__ counts) {
+  const uint32_t r = blockIdx.y;
+  if (r == rank) return;
+  const NeedPred pred{bm_all + (uint64_t)r * words, cl, world, rank};
+  unsigned long long acc = 0;
+  for (uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n_loc; l += (uint64_t)gridDim.x * blockDim.x) acc += pred((uint32_t)l);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(counts + r, acc);
+}
+
 struct IsEmpty { __host__ __device__ uint64_t operator()(uint32_t k) const { return k == 0xFFFFFFFFu ? 1ull : 0ull; } };
 
 inline unsigned grid_for(uint64_t items, unsigned block) { return (unsigned)((items + block - 1) / block); }
@@ -277,6 +308,7 @@ static void make_plans(const uint32_t* bounds, uint32_t n_loc, uint32_t nblk, co
 int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, uint32_t* ci_d) {
   lz_free_graph(c);
   c->epoch++;   // any cached CUDA graph of the step loop refers to the old matrix
+  c->graph_id++;
   c->orig_ro = ro_d; c->orig_ci = ci_d;
   c->n = n; c->nnz = nnz;
   const uint32_t world = (uint32_t)c->world, rank = (uint32_t)c->rank;
@@ -313,13 +345,13 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
   // Rows per rank and column blocks. A column block (= chunk) is `cl` rows of every rank: a window of world * cl
   // entries of the gathered vector that one SpMV pass gathers from; it is sized to stay L2-resident (64 MiB measured
   // best on C3, profiles/), and for world > 1 it is also the unit of the pipelined exchange. With the natural order the
-  // gathers are local anyway, so one GPU uses a single block.
+  // gathers are local anyway: a single block on any number of GPUs.
   uint64_t window = 64ull << 20;
   if (const char* e = getenv("LZ_SPMV_WINDOW_MB")) { long v = atol(e); if (v >= 1) window = (uint64_t)v << 20; }
   const uint64_t rows32 = (((n + world - 1) / world) + 31) & ~31ull;
   uint64_t cl = (window / 8 / world) & ~31ull;
   if (cl < 32) cl = 32;
-  if (natural && world == 1) cl = rows32;
+  if (natural) cl = rows32;   // one block: the gathers are local, and the exchange sends only the referenced entries (lz_build_push_lists)
   if (const char* e = getenv("LZ_SPMV_COLBLOCKS")) { int v = atoi(e); if (v >= 1) cl = (((rows32 + v - 1) / v) + 31) & ~31ull; }
   if (cl > rows32) cl = rows32;
   uint32_t nblk = (uint32_t)((rows32 + cl - 1) / cl);
@@ -481,6 +513,72 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
     LZ_CUDA(cudaStreamSynchronize(st));
   }
   LZ_CUDA(cudaGetLastError());
+  return LZ_OK;
+}
+
+
+// Needed-columns exchange, set up once per graph/vector allocation; collective over the NCCL communicator.
+// Every rank marks the columns its rows reference, the bitmaps are all-gathered, and each rank derives, per peer, the
+// ascending list of its own rows that the peer gathers from. When those lists are short (band-like / mesh-like graphs in
+// natural order: a halo plus a few chords) the Krylov vector is exchanged entry by entry over NVLink instead of in full
+// (k_scale_push_sparse); for graphs whose ranks reference most of each other's rows (R-MAT) the dense push stays.
+// The reference's two-card split copies the whole half vector every step (parallel-two-cards/lib/cu_lanczos.cu:116-165).
+int lz_build_push_lists(lz_ctx* c) {
+  cudaFree(c->push_list); c->push_list = nullptr;
+  c->sparse_push = false;
+  c->push_graph_id = c->graph_id;
+  for (int r = 0; r <= LZ_MAX_WORLD; r++) c->push_off[r] = 0;
+  if (c->world == 1 || !c->peer_push) return LZ_OK;
+  int force = -1;
+  if (const char* e = getenv("LZ_SPARSE_PUSH")) force = atoi(e) != 0;
+  cudaStream_t st = c->stream;
+  const uint32_t world = (uint32_t)c->world, rank = (uint32_t)c->rank;
+  const uint64_t n_pad = c->n_loc * (uint64_t)world, words = (n_pad + 31) / 32;
+  DevBuf bm, cnt_d;
+  LZ_CUDA(cudaMalloc(&bm.p, words * 4 * world));
+  LZ_CUDA(cudaMalloc(&cnt_d.p, sizeof(unsigned long long) * (LZ_MAX_WORLD + 1)));
+  uint32_t* mine = bm.as<uint32_t>() + (uint64_t)rank * words;
+  LZ_CUDA(cudaMemsetAsync(mine, 0, words * 4, st));
+  LZ_CUDA(cudaMemsetAsync(cnt_d.p, 0, sizeof(unsigned long long) * (LZ_MAX_WORLD + 1), st));
+  if (c->nnz_loc) k_mark_cols<<<(unsigned)c->sm_count * 8, 256, 0, st>>>(c->col, c->nnz_loc, mine);
+  LZ_NCCL(lz_nccl()->AllGather(mine, bm.p, words, ncclUint32, c->comm, st));
+  k_count_need<<<dim3((unsigned)c->sm_count * 2, world), 256, 0, st>>>(bm.as<uint32_t>(), words, c->n_loc, c->chunk_rows, world, rank,
+                                                                        (unsigned long long*)cnt_d.p);
+  unsigned long long cnt_h[LZ_MAX_WORLD + 1] = {};
+  LZ_CUDA(cudaMemcpyAsync(cnt_h, cnt_d.p, sizeof(unsigned long long) * world, cudaMemcpyDeviceToHost, st));
+  LZ_CUDA(cudaStreamSynchronize(st));
+  unsigned long long total = 0;
+  for (uint32_t r = 0; r < world; r++) total += cnt_h[r];
+  // the decision must be the same on every rank: compare the global volume with the dense one
+  double tot_d = (double)total;
+  double* buf = c->scal + 10;
+  LZ_CUDA(cudaMemcpyAsync(buf, &tot_d, 8, cudaMemcpyHostToDevice, st));
+  LZ_NCCL(lz_nccl()->AllReduce(buf, buf, 1, ncclDouble, ncclSum, c->comm, st));
+  LZ_CUDA(cudaMemcpyAsync(&tot_d, buf, 8, cudaMemcpyDeviceToHost, st));
+  LZ_CUDA(cudaStreamSynchronize(st));
+  const double dense = (double)world * (double)(world - 1) * (double)c->n_loc;
+  const bool sparse = force >= 0 ? force != 0 : tot_d < 0.5 * dense;
+  c->push_need_frac = dense > 0 ? tot_d / dense : 1.0;
+  if (!sparse) return LZ_OK;
+  if (total > 0xFFFFFFF0ull) return LZ_OK;   // offsets are 32-bit; such a graph is dense anyway
+  LZ_CUDA(cudaMalloc((void**)&c->push_list, (total ? total : 1) * 4));
+  DevBuf nsel, tmp;
+  LZ_CUDA(cudaMalloc(&nsel.p, 8));
+  size_t tb = 0;
+  cub::CountingInputIterator<uint32_t> it(0u);
+  LZ_CUDA(cub::DeviceSelect::If(nullptr, tb, it, c->push_list, nsel.as<int64_t>(), (int64_t)c->n_loc, NeedPred{bm.as<uint32_t>(), c->chunk_rows, world, rank}, st));
+  LZ_CUDA(cudaMalloc(&tmp.p, tb ? tb : 1));
+  uint64_t off = 0;
+  for (uint32_t r = 0; r < world; r++) {
+    c->push_off[r] = (uint32_t)off;
+    if (r == rank || cnt_h[r] == 0) continue;
+    LZ_CUDA(cub::DeviceSelect::If(tmp.p, tb, it, c->push_list + off, nsel.as<int64_t>(), (int64_t)c->n_loc,
+                                  NeedPred{bm.as<uint32_t>() + (uint64_t)r * words, c->chunk_rows, world, rank}, st));
+    off += cnt_h[r];
+  }
+  for (uint32_t r = world; r <= LZ_MAX_WORLD; r++) c->push_off[r] = (uint32_t)off;
+  LZ_CUDA(cudaStreamSynchronize(st));
+  c->sparse_push = true;
   return LZ_OK;
 }
 

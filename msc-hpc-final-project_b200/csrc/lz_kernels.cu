@@ -566,6 +566,59 @@ __global__ void __launch_bounds__(kBlock) k_scale_push(const double* __restrict_
   }
 }
 
+
+// Producer side of the needed-columns exchange (lz_build_push_lists): q_next = w / beta is stored locally and into this
+// rank's own slots of the gathered vector in full; every peer receives only the entries its rows reference (8-byte peer
+// stores over NVLink, ascending addresses). One arrival counter per chunk is raised at the end, as in k_scale_push, so the
+// consuming SpMV passes are unchanged. Remote values are recomputed from w (same division => same bits as the local copy).
+struct lz_push_lists {
+  const uint32_t* list;
+  uint32_t off[LZ_MAX_WORLD + 1];
+};
+__global__ void __launch_bounds__(kBlock) k_scale_push_sparse(const double* __restrict__ w, const double* __restrict__ norm2_p, uint64_t n,
+                                                              double* __restrict__ q_next, const __grid_constant__ lz_peers peers, uint64_t cl,
+                                                              uint32_t nchunks, uint32_t world, uint32_t rank, unsigned long long seq,
+                                                              unsigned int* ticket, double* beta_out, const __grid_constant__ lz_red red,
+                                                              const __grid_constant__ lz_push_lists lists) {
+  __shared__ double s_bcast;
+  __shared__ bool s_last;
+  const double beta = norm2_p ? sqrt(red.seq ? red_consume(red, 1, &s_bcast) : *norm2_p) : 1.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && beta_out) *beta_out = beta;
+  const double2* w2 = reinterpret_cast<const double2*>(w);
+  double2* q2 = reinterpret_cast<double2*>(q_next);
+  double* own = peers.x[rank];
+  const uint64_t n2 = n >> 1;
+  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
+    double2 v = w2[i];
+    if (norm2_p) { v.x /= beta; v.y /= beta; }
+    if (q_next != w) q2[i] = v;
+    *reinterpret_cast<double2*>(own + xfull_index(2 * i, cl, world, rank)) = v;
+  }
+  for (uint32_t r = 0; r < world; r++) {
+    if (r == rank) continue;
+    double* dst = peers.x[r];
+    const uint32_t e = lists.off[r + 1];
+    for (uint64_t t = (uint64_t)lists.off[r] + (uint64_t)blockIdx.x * kBlock + threadIdx.x; t < e; t += (uint64_t)gridDim.x * kBlock) {
+      const uint32_t l = __ldg(lists.list + t);
+      double v = w[l];
+      if (norm2_p) v /= beta;
+      dst[xfull_index(l, cl, world, rank)] = v;
+    }
+  }
+  __threadfence_system();          // this thread's peer stores are visible system-wide before the CTA reports in
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) {
+      *ticket = 0u;
+      __threadfence_system();
+      for (uint32_t c = 0; c < nchunks; c++)
+        for (uint32_t r = 0; r < world; r++) st_release_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, seq);
+    }
+  }
+}
+
 // q0_local[l] = x_orig[new2old[slot(l)]] / sqrt(norm2)
 __global__ void k_permute_in_local(const double* __restrict__ x_orig, const uint32_t* __restrict__ new2old, uint64_t n, uint64_t cl,
                                    uint32_t world, uint32_t rank, const double* __restrict__ norm2_p, double* __restrict__ dst) {
@@ -992,6 +1045,16 @@ int lz_k_scale_push(lz_ctx* c, const double* w, const double* norm2, double* q_n
                     uint32_t push_chunks, unsigned long long red_seq) {
   lz_peers peers;
   for (int r = 0; r < LZ_MAX_WORLD; r++) { peers.x[r] = c->peer_xfull[r]; peers.f[r] = c->peer_flags[r]; }
+  if (c->sparse_push) {            // needed-columns exchange: all chunks are sent (and flagged) by this one launch
+    lz_push_lists lists;
+    lists.list = c->push_list;
+    for (int r = 0; r <= LZ_MAX_WORLD; r++) lists.off[r] = c->push_off[r];
+    k_scale_push_sparse<<<stream_grid(c, c->n_loc / 2 + 1), kBlock, 0, c->stream>>>(w, norm2, c->n_loc, q_next, peers, c->chunk_rows, c->ncolblk,
+                                                                                   (uint32_t)c->world, (uint32_t)c->rank, seq, c->push_ticket,
+                                                                                   beta_out, make_red(c, red_seq), lists);
+    LZ_LAUNCH_CHECK();
+    return LZ_OK;
+  }
   // few CTAs suffice to saturate NVLink; cap so the per-chunk ticketing stays cheap
   unsigned g = stream_grid(c, c->chunk_rows / 2 + 1);
   const unsigned cap = (unsigned)c->sm_count * 2;

@@ -58,12 +58,45 @@ def main():
         x = np.random.default_rng(6).integers(-1000, 1000, n).astype(np.float64)
         assert np.array_equal(ctx.spmv_host(x), orc.spmv(ro, ci, x)), name
     del os.environ["LZ_ORDER"]
+    # needed-columns exchange, forced: every peer receives only the entries its rows reference (lists rebuilt per graph although
+    # n and the shard shape repeat), degree order and natural order, plain and with reorthogonalisation, several column blocks
+    os.environ["LZ_SPARSE_PUSH"] = "1"
+    for order, blocks in (("d", None), ("n", None), ("d", "3")):
+        os.environ["LZ_ORDER"] = order
+        if blocks:
+            os.environ["LZ_SPMV_COLBLOCKS"] = blocks
+        for name in ("band_n4096_k40", "rmat_s12_k30", "er_n257_k10_ragged"):
+            gl = np.load(os.path.join(gdir, name + ".npz"))
+            ro, ci, k, n = gl["row_offset"], gl["col_idx"], int(gl["k"]), int(gl["n"])
+            ctx.csr_upload(ro, ci)
+            y = ctx.expv_host(None, k)
+            mode, frac = ctx.exchange_info()
+            assert mode == lz.EXCHANGE_PEER_SPARSE and 0.0 < frac <= 1.0, (mode, frac)
+            assert rel2(y, gl["ans"]) < 1e-9, ("sparse", order, name, rel2(y, gl["ans"]))
+            assert np.array_equal(orc.top_k(y), orc.top_k(gl["ans"])), name
+            assert rel2(ctx.expv_host(gl["x_random"], k), gl["ans_random"]) < 1e-9, name
+            assert rel2(ctx.expv_host(None, k, lz.REORTH_FULL), gl["ans"]) < 1e-9, name
+        os.environ.pop("LZ_SPMV_COLBLOCKS", None)
+    del os.environ["LZ_ORDER"], os.environ["LZ_SPARSE_PUSH"]
+    # chosen from the data: a band-like graph large enough for the natural order sends a halo plus its chords, an R-MAT graph
+    # everything; the sparse and the dense exchange must give the same bits (same values, same summation order)
+    ctx.graph_generate(lz.GraphSpec.band(1 << 20, 5))
+    yb = ctx.expv_host(None, 20)
+    mode, frac = ctx.exchange_info()
+    assert mode == lz.EXCHANGE_PEER_SPARSE and frac < 0.1, (mode, frac)
+    os.environ["LZ_SPARSE_PUSH"] = "0"
+    ctx.graph_generate(lz.GraphSpec.band(1 << 20, 5))          # same shape: only the exchange lists are rebuilt
+    yd = ctx.expv_host(None, 20)
+    assert ctx.exchange_info()[0] == lz.EXCHANGE_PEER_DENSE
+    del os.environ["LZ_SPARSE_PUSH"]
+    assert np.array_equal(yb, yd) and np.all(np.isfinite(yb))
     # generated graph, compared with the CPU oracle
     spec = lz.GraphSpec.rmat(16, 8, 1)
     ctx.graph_generate(spec)
     ro, ci = ctx.csr_download()
     n = len(ro) - 1
     y = ctx.expv_host(None, 30)
+    assert ctx.exchange_info()[0] == lz.EXCHANGE_PEER_DENSE
     ref, _, _ = orc.expv(ro, ci, 30, np.ones(n))
     assert rel2(y, ref) < 1e-9 and np.array_equal(orc.top_k(y), orc.top_k(ref))
     # single-caller entry point: only rank 0 passes x and receives the answer
