@@ -301,6 +301,7 @@ static int create_body(lz_ctx* c, int device, int rank, int world, const void* u
   c->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("LZ_SPMV_VARIANT")) { int v = atoi(e); if (v >= 0 && v <= LZ_SPMV_WARP) c->spmv_variant = v; }     // tuning knob
   if (const char* e = getenv("LZ_SPMV_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) c->spmv_ctas_per_sm = (uint32_t)v; }   // tuning knob
+  if (const char* e = getenv("LZ_SELL_GROUP")) { int v = atoi(e); if (v == 1 || v == 4) c->sell_group_force = (uint32_t)v; }      // test knob
   LZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   LZ_CUDA(cudaEventCreate(&c->ev_a)); LZ_CUDA(cudaEventCreate(&c->ev_b));
   LZ_CUDA(cudaEventCreate(&c->ev_e0)); LZ_CUDA(cudaEventCreate(&c->ev_e1));

@@ -121,9 +121,11 @@ struct lz_ctx {
   uint32_t* sell_sp = nullptr;     // device, [ncolblk * n_items + 1]
   uint32_t* sell_col = nullptr;    // device
   uint64_t sell_entries = 0;       // padded entries stored (all blocks)
+  bool sell_narrow[LZ_MAX_COLBLK] = {};   // block b (natural order only): mean width of the 32-row slices <= 6 -> batched-quad instantiation of the kernel
   lz_spmv_plan plan_auto[LZ_MAX_COLBLK] = {}, plan_warp{};
   int spmv_variant = LZ_SPMV_AUTO;
   uint32_t spmv_ctas_per_sm = 6;   // persistent SpMV grid = sm_count * this
+  uint32_t sell_group_force = 0;   // 0 = automatic; 1 or 4 = items per work unit of the sliced kernel (LZ_SELL_GROUP, tests)
 
   // ---- vectors ----------------------------------------------------------------------------------------------------
   uint64_t vec_n = 0, vec_nloc = 0; // graph size the vectors below were allocated for

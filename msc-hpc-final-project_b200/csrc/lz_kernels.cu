@@ -333,8 +333,13 @@ __global__ void __launch_bounds__(kBlock) k_spmv_dot(const __grid_constant__ lz_
 // row" at a time. Either way the index stream is consumed as whole 128-byte lines (one L1 wavefront per 32 gathers),
 // there are no per-row pointer loads and — for the short-row items, i.e. almost all of the matrix — no shuffles: the
 // gathers themselves are all that is left on the SM's load path, which is what bounds this kernel (1 line/clk/SM).
+// NARROW (column blocks whose slices are only a few entries wide: band-like graphs in natural order, the cold column block
+// of a degree-sorted graph): a quad of up to 8-wide slices is processed 4 chunks x 4 items at a time, 16 gathers per lane
+// in flight instead of one slice's 3-6 — such a block is latency-bound otherwise. Costs registers (3 CTAs/SM instead of
+// 6), so it is a separate instantiation chosen per column block at ingest. Summation order per row is unchanged.
 constexpr int kSellU = 8;   // chunks (gathers per lane) in flight
-__global__ void __launch_bounds__(kBlock) k_spmv_sell(const uint32_t* __restrict__ sp, const uint32_t* __restrict__ scol, uint32_t n_long,
+template <bool NARROW>
+__global__ void __launch_bounds__(kBlock, NARROW ? 4 : 6) k_spmv_sell(const uint32_t* __restrict__ sp, const uint32_t* __restrict__ scol, uint32_t n_long,
                                                       uint32_t n_items, uint32_t n_loc, const double* __restrict__ x,
                                                       const double* __restrict__ q, double* __restrict__ w, double* partials,
                                                       unsigned int* ticket, double* alpha_out, int accumulate, int final_pass,
@@ -366,6 +371,44 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell(const uint32_t* __restrict
 #pragma unroll
     for (int t = 0; t < 5; t++) off[t] = (group == 4) ? __ldg(sp + min(first + t, n_items)) : 0u;
     const uint32_t wmax = max(max(off[1] - off[0], off[2] - off[1]), max(off[3] - off[2], off[4] - off[3]));
+    if (NARROW && group == 4 && wmax <= 8 && first >= n_long) {
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      for (uint32_t u0 = 0; u0 < wmax; u0 += 4) {
+        uint32_t cc[4][4];
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            cc[t][u] = (off[t] + u0 + u < off[t + 1]) ? __ldcs(scol + (uint64_t)(off[t] + u0 + u) * 32 + lane) : 0xFFFFFFFFu;
+        double vv[4][4];
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+          for (int u = 0; u < 4; u++) vv[t][u] = (cc[t][u] != 0xFFFFFFFFu) ? __ldg(x + cc[t][u]) : 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+          for (int u = 0; u < 4; u++) acc[t] += vv[t][u];
+      }
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const uint32_t item = first + t;
+        const uint32_t row = n_long + (item - n_long) * 32 + lane;
+        if (item < n_items && row < n_loc) {
+          double a = acc[t];
+          if (accumulate) {
+            if (final_pass || off[t + 1] > off[t]) {
+              a += w[row];
+              w[row] = a;
+            }
+          } else {
+            w[row] = a;
+          }
+          if (final_pass) d += a * q[row];
+        }
+      }
+      continue;
+    }
     if (group == 4 && wmax <= 2 && first >= n_long) {
       uint32_t cc[4][2];
 #pragma unroll
@@ -1000,15 +1043,19 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
     if (c->chunks_in_flight) LZ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_chunk[blk], 0));
     if (c->spmv_variant == LZ_SPMV_AUTO) {          // sliced layout: long rows warp-per-row, short rows 32 per warp
       uint32_t grid = (uint32_t)c->sm_count * c->spmv_ctas_per_sm;
-      const uint32_t group = (c->n_items >= 64u * grid * kWarps) ? 4u : 1u;   // quads only when every warp still gets >= 16 of them
+      uint32_t group = (c->n_items >= 64u * grid * kWarps) ? 4u : 1u;   // quads only when every warp still gets >= 16 of them
+      if (c->sell_group_force) group = c->sell_group_force;              // test knob (LZ_SELL_GROUP): small inputs through the quad paths
+      const bool narrow = c->sell_narrow[blk] && group == 4;
+      if (narrow && c->spmv_ctas_per_sm > 4) grid = (uint32_t)c->sm_count * 4;   // 64 registers: 4 resident CTAs per SM, one wave
       const uint32_t need = ((c->n_items + group - 1) / group + kWarps - 1) / kWarps;
       if (grid > need) grid = need;
       if (grid < 1) grid = 1;
       LZ_TRY(ensure_partials(c, grid));
       grid += job.nctas;
-      k_spmv_sell<<<grid, kBlock, 0, c->stream>>>(c->sell_sp + (uint64_t)blk * c->n_items, c->sell_col, c->n_long, c->n_items,
-                                                  (uint32_t)c->n_loc, x_gather, q_local, w_out, c->partials, c->ticket + 0, alpha_out, acc, fin,
-                                                  c->flags, blk, (uint32_t)c->world, wait_seq, job, group, red);
+      auto kern = narrow ? k_spmv_sell<true> : k_spmv_sell<false>;
+      kern<<<grid, kBlock, 0, c->stream>>>(c->sell_sp + (uint64_t)blk * c->n_items, c->sell_col, c->n_long, c->n_items,
+                                           (uint32_t)c->n_loc, x_gather, q_local, w_out, c->partials, c->ticket + 0, alpha_out, acc, fin,
+                                           c->flags, blk, (uint32_t)c->world, wait_seq, job, group, red);
     } else {                                         // CSR: vector (sub-warp) per row by degree bin, or warp per row
       const lz_spmv_plan& plan = (c->spmv_variant == LZ_SPMV_WARP) ? c->plan_warp : c->plan_auto[blk];
       if (plan.nitems == 0) return lz_fail(LZ_ERR_ARG, "empty SpMV plan");

@@ -80,6 +80,33 @@ def test_spmv_bit_exact_on_integer_data(lz, orc, ctx, spec_name, variant):
         ctx.set_spmv_variant(lz.SPMV_AUTO)
 
 
+@pytest.mark.parametrize("narrow", ["0", "1"])
+@pytest.mark.parametrize("blocks", ["1", "3"])
+def test_sliced_kernel_quad_paths_on_small_inputs(lz, orc, monkeypatch, narrow, blocks):
+    """The batched-quad paths of the sliced kernel (4 slices per work unit; the NARROW instantiation handles slices up to 8
+    wide 4 chunks x 4 slices at a time) normally switch on only at ~10^7 rows. Forced here on small ragged inputs, with one
+    and with several column blocks, in both vertex orders: SpMV must stay bit-exact and e^A x within tolerance."""
+    monkeypatch.setenv("LZ_SELL_GROUP", "4")
+    monkeypatch.setenv("LZ_SELL_NARROW", narrow)
+    monkeypatch.setenv("LZ_SPMV_COLBLOCKS", blocks)
+    specs = [lz.GraphSpec.er(30011, 150000, 5), lz.GraphSpec.rmat(15, 8, 3), lz.GraphSpec.band(20000, 9), lz.GraphSpec.er(33, 40, 1),
+             lz.GraphSpec.er(4099, 9000, 2)]
+    for order in ("d", "n"):
+        monkeypatch.setenv("LZ_ORDER", order)
+        with lz.Context(0) as c:
+            for spec in specs:
+                n, ro, ci = lz.generate_host(spec)
+                c.csr_upload(ro, ci)
+                x = np.random.default_rng(7).integers(-(1 << 20), 1 << 20, n).astype(np.float64)
+                assert np.array_equal(c.spmv_host(x), orc.spmv(ro, ci, x))
+                assert np.array_equal(c.spmv_host(np.ones(n)), np.diff(ro).astype(np.float64))
+            n, ro, ci = lz.generate_host(specs[1])
+            c.csr_upload(ro, ci)
+            y = c.expv_host(None, 20)
+            ref, _, _ = orc.expv(ro, ci, 20, np.ones(n))
+            assert rel2(y, ref) < TOL and np.array_equal(orc.top_k(y), orc.top_k(ref))
+
+
 @pytest.mark.parametrize("spec_name", ["er", "rmat", "band"])
 def test_device_generator_matches_host_generator(lz, ctx, spec_name):
     spec = {"er": lz.GraphSpec.er(50000, 300000, 11), "rmat": lz.GraphSpec.rmat(16, 8, 1),
