@@ -129,6 +129,10 @@ int lz_get_eigen(lz_ctx* ctx, double* eigvals_out, double* eigvecs_out, double* 
 /* Convergence estimate: relative 2-norm change of e^A x between Krylov dimensions k_prev < k (k = the last run), from the
  * tridiagonal alone (no pass over the basis). The reference has no such check; its author recommends one (writeup sec. 11). */
 int lz_estimate_change(lz_ctx* ctx, uint32_t k_prev, double* rel_out);
+/* The smallest Krylov dimension k' <= k (k = the last run) such that every dimension in [k', k] reproduces the k-step answer to
+ * within `tol` (relative 2-norm, by the estimate above). *k_out == k: not even k-1 steps do, convergence at k is not demonstrated;
+ * *est_out (optional) is the estimate at *k_out, or at k-1 in that case. The reference fixes k by hand (main.cu:28, -k). */
+int lz_choose_k(lz_ctx* ctx, double tol, uint32_t* k_out, double* est_out);
 /* ans = V * c as a tall-skinny GEMV on the device. Replaces multOut's cblas_dgemv (multiplyOut.cu:43-47) and
  * cu_multOut's cublasDgemv (parallel-mult-on-card/lib/cu_multiplyOut.cu:66-72). Enqueue only. */
 int lz_multout(lz_ctx* ctx);

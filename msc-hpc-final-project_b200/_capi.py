@@ -94,6 +94,7 @@ _sig("lz_get_tridiag", _ctx, _f64p, _f64p)
 _sig("lz_tridiag_expv", _ctx)
 _sig("lz_get_eigen", _ctx, _f64p, _f64p, _f64p)
 _sig("lz_estimate_change", _ctx, C.c_uint32, _P(C.c_double))
+_sig("lz_choose_k", _ctx, C.c_double, _P(C.c_uint32), _P(C.c_double))
 _sig("lz_multout", _ctx)
 _sig("lz_get_ans", _ctx, _f64p)
 _sig("lz_expv_host", _ctx, _f64p, C.c_uint32, C.c_int, _f64p)
@@ -269,6 +270,12 @@ class Context:
         r = C.c_double(0)
         _check(lib.lz_estimate_change(self._h, k_prev, C.byref(r)))
         return r.value
+
+    def choose_k(self, tol):
+        """(k', estimate): smallest Krylov dimension whose answer stays within tol of the last run's, by the estimate."""
+        k, est = C.c_uint32(0), C.c_double(0)
+        _check(lib.lz_choose_k(self._h, tol, C.byref(k), C.byref(est)))
+        return k.value, est.value
 
     def multout(self):
         _check(lib.lz_multout(self._h))

@@ -587,38 +587,84 @@ extern "C" int lz_get_eigen(lz_ctx* c, double* eigvals_out, double* eigvecs_out,
 // A-posteriori convergence estimate (the author's own recommendation, writeup section 11): with an orthonormal basis,
 // || y_k - y_k' ||_2 = || c_k - [c_k'; 0] ||_2, so the change of the answer between Krylov dimensions k' < k costs two
 // k x k eigen-solves and no pass over the basis.
+namespace {
+struct CoefSolver {   // scratch for solves of leading blocks of the current tridiagonal; nothing of the ctx's result is touched
+  lz_ctx* c;
+  uint32_t k;
+  double *ev = nullptr, *evec = nullptr, *work = nullptr, *coef = nullptr;
+  int* st = nullptr;
+  CoefSolver(lz_ctx* c_, uint32_t k_) : c(c_), k(k_) {}
+  ~CoefSolver() { cudaFree(ev); cudaFree(evec); cudaFree(work); cudaFree(coef); cudaFree(st); }
+  int init() {
+    LZ_CUDA(cudaMalloc((void**)&ev, k * 8)); LZ_CUDA(cudaMalloc((void**)&evec, (size_t)k * k * 8));
+    LZ_CUDA(cudaMalloc((void**)&work, (size_t)k * k * 8)); LZ_CUDA(cudaMalloc((void**)&coef, k * 8));
+    LZ_CUDA(cudaMalloc((void**)&st, sizeof(int)));
+    return LZ_OK;
+  }
+  int solve(uint32_t kk, std::vector<double>& out) {   // out = c_kk (kk entries)
+    out.assign(kk, 0.0);
+    int sth = 0;
+    LZ_TRY(lz_k_tridiag_expv_into(c, kk, ev, evec, work, coef, st));
+    LZ_CUDA(cudaMemcpyAsync(out.data(), coef, kk * 8, cudaMemcpyDeviceToHost, c->stream));
+    LZ_CUDA(cudaMemcpyAsync(&sth, st, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LZ_CUDA(cudaStreamSynchronize(c->stream));
+    if (sth) return lz_fail(LZ_ERR_NUMERIC, "tridiagonal solve of the leading %u x %u block failed or overflowed (status %d)", kk, kk, sth);
+    return LZ_OK;
+  }
+};
+double rel_change(const std::vector<double>& a, const std::vector<double>& b) {   // || a - [b; 0] || / || a ||
+  double num = 0.0, den = 0.0;
+  for (size_t i = 0; i < a.size(); i++) {
+    const double d = a[i] - (i < b.size() ? b[i] : 0.0);
+    num += d * d;
+    den += a[i] * a[i];
+  }
+  return den > 0.0 ? sqrt(num / den) : 0.0;
+}
+}  // namespace
+
 extern "C" int lz_estimate_change(lz_ctx* c, uint32_t k_prev, double* rel_out) {
   if (!c || !rel_out) return lz_fail(LZ_ERR_ARG, "null argument");
   if (!c->have_tridiag) return lz_fail(LZ_ERR_ARG, "lz_lanczos_run must be called before lz_estimate_change");
   const uint32_t k = c->k_done;
   if (k_prev < 1 || k_prev >= k) return lz_fail(LZ_ERR_ARG, "k_prev must be in [1, %u)", k);
   LZ_TRY(set_dev(c));
-  double *ev = nullptr, *evec = nullptr, *work = nullptr, *coef = nullptr;
-  int* st = nullptr;
-  LZ_CUDA(cudaMalloc((void**)&ev, k * 8)); LZ_CUDA(cudaMalloc((void**)&evec, (size_t)k * k * 8));
-  LZ_CUDA(cudaMalloc((void**)&work, (size_t)k * k * 8)); LZ_CUDA(cudaMalloc((void**)&coef, 2 * k * 8));
-  LZ_CUDA(cudaMalloc((void**)&st, 2 * sizeof(int)));
-  std::vector<double> a(k), b(k_prev);
-  int sth[2] = {0, 0};
-  int rc = LZ_OK;
-  do {
-    if ((rc = lz_k_tridiag_expv_into(c, k, ev, evec, work, coef, st)) != LZ_OK) break;
-    if ((rc = lz_k_tridiag_expv_into(c, k_prev, ev, evec, work, coef + k, st + 1)) != LZ_OK) break;
-    if (cudaMemcpyAsync(a.data(), coef, k * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-        cudaMemcpyAsync(b.data(), coef + k, k_prev * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-        cudaMemcpyAsync(sth, st, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-        cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = lz_fail(LZ_ERR_CUDA, "read-back of the coefficient vectors failed"); break; }
-  } while (0);
-  cudaFree(ev); cudaFree(evec); cudaFree(work); cudaFree(coef); cudaFree(st);
-  if (rc != LZ_OK) return rc;
-  if (sth[0] || sth[1]) return lz_fail(LZ_ERR_NUMERIC, "tridiagonal solve failed or overflowed (status %d / %d)", sth[0], sth[1]);
-  double num = 0.0, den = 0.0;
-  for (uint32_t i = 0; i < k; i++) {
-    const double d = a[i] - (i < k_prev ? b[i] : 0.0);
-    num += d * d;
-    den += a[i] * a[i];
+  CoefSolver sv(c, k);
+  LZ_TRY(sv.init());
+  std::vector<double> a, b;
+  LZ_TRY(sv.solve(k, a));
+  LZ_TRY(sv.solve(k_prev, b));
+  *rel_out = rel_change(a, b);
+  return LZ_OK;
+}
+
+// Smallest Krylov dimension that would have sufficed: scans k' = k-1, k-2, ... while the estimated change of the answer
+// between k' and k stays <= tol, so every dimension from *k_out up to k meets the tolerance. *k_out == k means that not even
+// k-1 steps reproduce the k-step answer to tol, i.e. convergence at k is not demonstrated; *est_out is the estimate at
+// max(*k_out, 1) .. or at k-1 in that case. Costs (k - *k_out + 2) small solves on the device and no pass over the basis.
+extern "C" int lz_choose_k(lz_ctx* c, double tol, uint32_t* k_out, double* est_out) {
+  if (!c || !k_out) return lz_fail(LZ_ERR_ARG, "null argument");
+  if (!(tol > 0.0)) return lz_fail(LZ_ERR_ARG, "tol must be positive");
+  if (!c->have_tridiag) return lz_fail(LZ_ERR_ARG, "lz_lanczos_run must be called before lz_choose_k");
+  const uint32_t k = c->k_done;
+  LZ_TRY(set_dev(c));
+  *k_out = k;
+  if (est_out) *est_out = 0.0;
+  if (k < 2) return LZ_OK;
+  CoefSolver sv(c, k);
+  LZ_TRY(sv.init());
+  std::vector<double> a, b;
+  LZ_TRY(sv.solve(k, a));
+  for (uint32_t kp = k - 1; kp >= 1; kp--) {
+    LZ_TRY(sv.solve(kp, b));
+    const double est = rel_change(a, b);
+    if (est > tol) {
+      if (kp == k - 1 && est_out) *est_out = est;
+      break;
+    }
+    *k_out = kp;
+    if (est_out) *est_out = est;
   }
-  *rel_out = den > 0.0 ? sqrt(num / den) : 0.0;
   return LZ_OK;
 }
 

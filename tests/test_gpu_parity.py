@@ -350,6 +350,20 @@ def test_convergence_estimate_matches_actual_change(lz, orc, golden, ctx):
     assert est[8] > est[12] > est[16]
     with pytest.raises(lz.LzError):
         ctx.estimate_change(20)
+    # lz_choose_k: the smallest k' whose whole tail [k', k) meets the tolerance, consistent with the point estimates
+    for tol in (1e-6, 1e-10, 1e-13):
+        kc, e = ctx.choose_k(tol)
+        assert 1 <= kc <= 20
+        if kc < 20:
+            assert e <= tol and all(ctx.estimate_change(kp) <= tol for kp in range(kc, 20))
+            if kc > 1:
+                assert ctx.estimate_change(kc - 1) > tol
+            yk, _, _ = orc.expv(ro, ci, kc, np.ones(n))
+            assert rel2(yk, y20) <= max(10 * tol, 1e-12)
+    assert ctx.choose_k(1e-6)[0] <= ctx.choose_k(1e-10)[0] <= ctx.choose_k(1e-13)[0]
+    assert ctx.choose_k(1e-300)[0] == 20            # nothing short of k reproduces the k-step answer that closely
+    with pytest.raises(lz.LzError):
+        ctx.choose_k(0.0)
 
 
 @pytest.mark.parametrize("always", ["0", "1"])
