@@ -164,6 +164,9 @@ def main():
         args.gpus = world
     w = dict(WORKLOADS[args.workload])
     k = args.k or w["k"]
+    overrides = [f"{a}={v}" for a, v in (("scale", args.scale), ("n", args.n), ("k", args.k)) if v]
+    if overrides:                                  # debug overrides must not masquerade as the named config
+        w["name"] += " [override: " + ", ".join(overrides) + "]"
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     lz = graft.load_package()
