@@ -372,14 +372,20 @@ __global__ void __launch_bounds__(kBlock, NARROW ? 4 : 6) k_spmv_sell(const uint
     for (int t = 0; t < 5; t++) off[t] = (group == 4) ? __ldg(sp + min(first + t, n_items)) : 0u;
     const uint32_t wmax = max(max(off[1] - off[0], off[2] - off[1]), max(off[3] - off[2], off[4] - off[3]));
     if (NARROW && group == 4 && wmax <= 8 && first >= n_long) {
+      // one base pointer and one width per slice; the two rounds are unrolled so every index load is base + immediate
+      const uint32_t* pt[4];
+      uint32_t wd[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) { wd[t] = off[t + 1] - off[t]; pt[t] = scol + (uint64_t)off[t] * 32 + lane; }
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      for (uint32_t u0 = 0; u0 < wmax; u0 += 4) {
+#pragma unroll
+      for (int round = 0; round < 2; round++) {
+        if (round == 1 && wmax <= 4) break;
         uint32_t cc[4][4];
 #pragma unroll
         for (int t = 0; t < 4; t++)
 #pragma unroll
-          for (int u = 0; u < 4; u++)
-            cc[t][u] = (off[t] + u0 + u < off[t + 1]) ? __ldcs(scol + (uint64_t)(off[t] + u0 + u) * 32 + lane) : 0xFFFFFFFFu;
+          for (int u = 0; u < 4; u++) cc[t][u] = ((uint32_t)(round * 4 + u) < wd[t]) ? __ldcs(pt[t] + (round * 4 + u) * 32) : 0xFFFFFFFFu;
         double vv[4][4];
 #pragma unroll
         for (int t = 0; t < 4; t++)
