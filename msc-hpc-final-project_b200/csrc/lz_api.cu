@@ -70,7 +70,9 @@ void free_vectors(lz_ctx* c) {
   c->flags = nullptr; c->push_ticket = nullptr; c->gfull = nullptr;
   cudaFree(c->V); cudaFree(c->w); cudaFree(c->xfull); cudaFree(c->xstage); cudaFree(c->ans);
   cudaFree(c->alpha); cudaFree(c->beta); cudaFree(c->hcoef); cudaFree(c->eigvals); cudaFree(c->eigvecs); cudaFree(c->eigwork);
-  cudaFree(c->coef);
+  cudaFree(c->coef); cudaFree(c->norm2v);
+  c->norm2v = nullptr;
+  c->lagged_done = false;
   c->V = c->w = c->xfull = c->xstage = c->ans = c->alpha = c->beta = c->hcoef = c->eigvals = c->eigvecs = c->eigwork = c->coef = nullptr;
   c->k_cap = 0;
   c->have_x = c->have_tridiag = c->have_coef = c->have_ans = false;
@@ -195,6 +197,9 @@ int ensure_k(lz_ctx* c, uint32_t k) {
   cudaFree(c->V);
   c->V = nv;
   cudaFree(c->alpha); cudaFree(c->beta); cudaFree(c->hcoef); cudaFree(c->eigvals); cudaFree(c->eigvecs); cudaFree(c->eigwork); cudaFree(c->coef);
+  cudaFree(c->norm2v);
+  c->lagged_done = false;
+  LZ_CUDA(cudaMalloc((void**)&c->norm2v, (k + 1) * 8));
   LZ_CUDA(cudaMalloc((void**)&c->alpha, k * 8)); LZ_CUDA(cudaMalloc((void**)&c->beta, k * 8));
   LZ_CUDA(cudaMalloc((void**)&c->hcoef, k * 8)); LZ_CUDA(cudaMalloc((void**)&c->eigvals, k * 8));
   LZ_CUDA(cudaMalloc((void**)&c->eigvecs, (uint64_t)k * k * 8)); LZ_CUDA(cudaMalloc((void**)&c->eigwork, (uint64_t)k * k * 8));
@@ -301,6 +306,7 @@ static int create_body(lz_ctx* c, int device, int rank, int world, const void* u
   c->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("LZ_SPMV_VARIANT")) { int v = atoi(e); if (v >= 0 && v <= LZ_SPMV_WARP) c->spmv_variant = v; }     // tuning knob
   if (const char* e = getenv("LZ_SPMV_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) c->spmv_ctas_per_sm = (uint32_t)v; }   // tuning knob
+  if (const char* e = getenv("LZ_LAGGED_NORM")) c->lagged = atoi(e) != 0;
   if (const char* e = getenv("LZ_SELL_GROUP")) { int v = atoi(e); if (v == 1 || v == 4) c->sell_group_force = (uint32_t)v; }      // test knob
   LZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   LZ_CUDA(cudaEventCreate(&c->ev_a)); LZ_CUDA(cudaEventCreate(&c->ev_b));
@@ -419,6 +425,25 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
   const uint64_t ldv = c->ldv;
   const bool dist = c->world > 1;
   LZ_CUDA(cudaMemsetAsync(c->status + 2, 0, sizeof(int), c->stream));
+  if (!dist && !reorth && c->lagged) {
+    // Lagged normalisation: 2 SpMV passes + ONE vector kernel per step; row j >= 1 of V keeps u_j unnormalised with
+    // norm2v[j] = ||u_j||^2 (row 0 is the normalised start vector). See k_update_lagged.
+    LZ_TRY(lz_k_fill(c, c->norm2v, 1, 1.0));
+    for (uint32_t j = 0; j < k; j++) {
+      double* uj = c->V + (uint64_t)j * ldv;
+      {  // t = A u_j ; alpha_j = (t . u_j) / ||u_j||^2
+        Scope s(c, 0);
+        LZ_TRY(lz_k_spmv_dot(c, uj, uj, c->w, c->alpha + j, 0ull, nullptr, 0ull, c->norm2v + j));
+      }
+      if (j + 1 == k) break;
+      {  // u_{j+1} = t/||u_j|| - alpha_j q_j - beta_{j-1} q_{j-1} ; ||u_{j+1}||^2 ; beta_j
+        Scope s(c, 1);
+        LZ_TRY(lz_k_update_lagged(c, c->w, uj, j ? uj - ldv : nullptr, c->alpha + j, c->norm2v + j, j ? c->norm2v + (j - 1) : nullptr,
+                                  uj + ldv, c->norm2v + (j + 1), c->beta + j));
+      }
+    }
+    return LZ_OK;
+  }
   if (dist) {   // q_0 into the gathered buffer (a previous run left q_{k-1} there)
     if (c->peer_push) {
       LZ_TRY(lz_k_scale_push(c, c->V, nullptr, c->V, nullptr, ++c->push_seq, fused_push ? 1u : c->ncolblk));
@@ -536,6 +561,7 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
   if (!done) LZ_TRY(enqueue_steps(c, k, reorth, fused_push, peer_scalars));
   LZ_CUDA(cudaEventRecord(c->ev_b, c->stream));
   c->k_done = k;
+  c->lagged_done = c->world == 1 && !reorth && c->lagged;
   c->reorth_done = reorth;
   c->have_tridiag = true;
   c->have_coef = c->have_ans = false;
@@ -673,13 +699,18 @@ extern "C" int lz_multout(lz_ctx* c) {
   if (!c->have_coef) return lz_fail(LZ_ERR_ARG, "lz_tridiag_expv must be called before lz_multout");
   LZ_TRY(set_dev(c));
   LZ_CUDA(cudaEventRecord(c->ev_m0, c->stream));
-  LZ_TRY(lz_k_combine(c, c->V, c->k_done, c->coef, 1.0, nullptr, c->ans, nullptr));
+  const double* coef = c->coef;
+  if (c->lagged_done) {   // rows 1.. of V are unnormalised: fold 1/||u_j|| into the coefficients
+    LZ_TRY(lz_k_coef_scale(c, c->coef, c->norm2v, c->k_done, c->hcoef));
+    coef = c->hcoef;
+  }
+  LZ_TRY(lz_k_combine(c, c->V, c->k_done, coef, 1.0, nullptr, c->ans, nullptr));
   LZ_CUDA(cudaEventRecord(c->ev_m1, c->stream));
   c->have_ans = true;
   return LZ_OK;
 }
 
-static int gather_to_host(lz_ctx* c, const double* local, double* host_out) {
+static int gather_to_host(lz_ctx* c, const double* local, double* host_out, const double* norm2_div = nullptr) {
   // local [n_loc] (new order, this rank's slice) -> host [n] original order, on every rank
   const double* full = local;
   if (c->world > 1) {
@@ -689,6 +720,7 @@ static int gather_to_host(lz_ctx* c, const double* local, double* host_out) {
   }
   if (host_out) {   // ranks that do not need the vector on the host still take part in the gather above
     LZ_TRY(lz_k_permute_out(c, full, c->xstage));
+    if (norm2_div) LZ_TRY(lz_k_div_sqrt(c, c->xstage, c->n, norm2_div));
     LZ_CUDA(cudaMemcpyAsync(host_out, c->xstage, c->n * 8, cudaMemcpyDeviceToHost, c->stream));
   }
   LZ_CUDA(cudaStreamSynchronize(c->stream));
@@ -749,7 +781,8 @@ extern "C" int lz_get_basis(lz_ctx* c, uint32_t j, double* q_host) {
   if (!c || !q_host) return lz_fail(LZ_ERR_ARG, "null argument");
   if (!c->have_x || j >= (c->have_tridiag ? c->k_done : 1u)) return lz_fail(LZ_ERR_ARG, "basis vector %u not available", j);
   LZ_TRY(set_dev(c));
-  return gather_to_host(c, c->V + (uint64_t)j * c->ldv, q_host);
+  // after a lagged-normalisation run rows 1.. hold u_j = ||u_j|| q_j
+  return gather_to_host(c, c->V + (uint64_t)j * c->ldv, q_host, (c->lagged_done && c->have_tridiag && j > 0) ? c->norm2v + j : nullptr);
 }
 
 extern "C" int lz_set_profiling(lz_ctx* c, int on) {

@@ -139,6 +139,9 @@ struct lz_ctx {
   double* ans = nullptr;           // device, [n_loc]
   double* alpha = nullptr;         // device, [k_cap]
   double* beta = nullptr;          // device, [k_cap]
+  double* norm2v = nullptr;        // device, [k_cap + 1]: ||V[j]||^2 of the last run when the basis is stored unnormalised (lagged_done)
+  bool lagged = true;              // use the lagged normalisation where it applies (one GPU, no reorthogonalisation); LZ_LAGGED_NORM=0 disables
+  bool lagged_done = false;        // the last run left rows 1.. of V unnormalised
   double* scal = nullptr;          // device scalars: [0]=alpha acc, [1]=norm2 acc, [2]=x_norm, [3..] spare
   double* partials = nullptr;      // device, per-CTA partial sums
   uint32_t partials_cap = 0;
@@ -177,7 +180,13 @@ int lz_build_push_lists(lz_ctx* c);   // collective; call after the peers are ma
 int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out /* device scalar or null */,
                   unsigned long long wait_seq = 0 /* > 0: pass b first waits until chunk b of x_gather has arrived from every rank */,
                   const double* push_src = nullptr /* sliced variant only: pass b also sends chunk b + 1 of this local vector */,
-                  unsigned long long red_seq = 0 /* > 0 (sliced variant): alpha partial is published to all ranks instead of stored */);
+                  unsigned long long red_seq = 0 /* > 0 (sliced variant): alpha partial is published to all ranks instead of stored */,
+                  const double* alpha_div = nullptr /* device scalar: alpha_out = (w . q) / *alpha_div (lagged normalisation) */);
+// lagged normalisation (one GPU, plain recurrence): see k_update_lagged
+int lz_k_update_lagged(lz_ctx* c, const double* t, const double* uj, const double* uprev, const double* alpha, const double* norm2_j,
+                       const double* norm2_prev, double* u_next, double* norm2_out, double* beta_out);
+int lz_k_coef_scale(lz_ctx* c, const double* coef, const double* norm2, uint32_t k, double* out);
+int lz_k_div_sqrt(lz_ctx* c, double* v, uint64_t n, const double* norm2);
 int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev, double* alpha, const double* beta_prev,
                      double* norm2_out /* device scalar or null */, unsigned long long red_seq = 0 /* > 0: scalars go through the peer exchange */);
 // q_next = w / sqrt(*norm2); when xfull != null also stores it into this rank's slots of the chunk-major gathered vector

@@ -98,7 +98,7 @@ __device__ __forceinline__ double red_consume(const lz_red& red, int kind, doubl
 // `gridDim.x` partials in index order (strided per thread, then a fixed tree) and stores op(sum) to *out.
 __device__ __forceinline__ void grid_sum_finish(double cta_val, double* partials, unsigned int* ticket, double* out, double* sm,
                                                 bool* s_last, unsigned int cta = 0xFFFFFFFFu, unsigned int nctas = 0,
-                                                const lz_red* red = nullptr, int kind = 0) {
+                                                const lz_red* red = nullptr, int kind = 0, const double* out_div = nullptr) {
   if (cta == 0xFFFFFFFFu) { cta = blockIdx.x; nctas = gridDim.x; }   // default: every CTA of the grid takes part
   if (threadIdx.x == 0) {
     partials[cta] = cta_val;
@@ -114,7 +114,7 @@ __device__ __forceinline__ void grid_sum_finish(double cta_val, double* partials
     acc = block_sum(acc, sm);
     if (threadIdx.x == 0) {
       if (red && red->seq) red_publish(*red, kind, acc);   // multi-GPU: the partial goes to every rank's exchange area
-      else *out = acc;
+      else *out = out_div ? acc / *out_div : acc;   // lagged normalisation: alpha = (A u . u) / ||u||^2
       *ticket = 0u;
     }
   }
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_dot(const __grid_constant__ lz_
                                                      const double* __restrict__ x, const double* __restrict__ q, double* __restrict__ w,
                                                      double* partials, unsigned int* ticket, double* alpha_out, int accumulate,
                                                      int final_pass, const unsigned long long* flags, uint32_t blk, uint32_t world,
-                                                     unsigned long long wait_seq) {
+                                                     unsigned long long wait_seq, const double* alpha_div) {
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
   wait_chunk(flags, blk, world, wait_seq);
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_dot(const __grid_constant__ lz_
   }
   if (fin) {
     d = block_sum(d, sm);
-    grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last);
+    grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last, 0xFFFFFFFFu, 0, nullptr, 0, alpha_div);
   }
 }
 
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kBlock, NARROW ? 4 : 6) k_spmv_sell(const uint
                                                       unsigned int* ticket, double* alpha_out, int accumulate, int final_pass,
                                                       const unsigned long long* flags, uint32_t blk, uint32_t world,
                                                       unsigned long long wait_seq, const __grid_constant__ lz_push_job job,
-                                                      uint32_t group, const __grid_constant__ lz_red red) {
+                                                      uint32_t group, const __grid_constant__ lz_red red, const double* alpha_div) {
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
   // Fused exchange: the first job.nctas CTAs of pass `blk` send chunk job.chunk (= blk + 1) of the new Krylov vector to
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kBlock, NARROW ? 4 : 6) k_spmv_sell(const uint
   }
   if (final_pass) {
     d = block_sum(d, sm);
-    grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last, cta, nctas, &red, 0);
+    grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last, cta, nctas, &red, 0, alpha_div);
   }
 }
 
@@ -545,6 +545,79 @@ __global__ void __launch_bounds__(kBlock) k_update_norm(double* __restrict__ w, 
   }
   acc = block_sum(acc, sm);
   if (norm2_out) grid_sum_finish(acc, partials, ticket, norm2_out, sm, &s_last, 0xFFFFFFFFu, 0, &red, 1);
+}
+
+// Lagged normalisation (one GPU, plain recurrence): the basis row j >= 1 holds the UNNORMALISED vector u_j = w' of step
+// j-1 and norm2[j] = ||u_j||^2, so q_j = u_j / ||u_j|| is formed on the fly and the separate normalisation pass (read w,
+// write q: 16 bytes per row and one launch per step) disappears. With t = A u_j and alpha_j = (t . u_j) / ||u_j||^2:
+//   u_{j+1} = t/||u_j|| - alpha_j q_j - beta_{j-1} q_{j-1},   beta_{j-1} = ||u_j||,   beta_j = ||u_{j+1}||
+// which is the reference's recurrence (lanczos.cu:32-50) with the division by beta moved to the consumers (as a multiplication
+// by the reciprocal: results differ from the divide-first order in the last bit only).
+__global__ void __launch_bounds__(kBlock) k_update_lagged(const double* __restrict__ t, const double* __restrict__ uj, const double* __restrict__ up,
+                                                          const double* __restrict__ alpha_p, const double* __restrict__ norm2_j,
+                                                          const double* __restrict__ norm2_p, uint64_t n, double* __restrict__ u_next,
+                                                          double* partials, unsigned int* ticket, double* norm2_out, double* beta_out) {
+  __shared__ double sm[kWarps];
+  __shared__ bool s_last;
+  // u_{j+1} = (t - alpha u_j) / ||u_j|| - (||u_j|| / ||u_{j-1}||) u_{j-1}: the two scalars are formed once per thread, so the
+  // pass costs three multiply-adds per entry and stays HBM-bound (per-entry fp64 divisions made it compute-bound: measured).
+  const double a = *alpha_p;
+  const double nj = sqrt(*norm2_j);
+  const double rj = 1.0 / nj;
+  const double cp = up ? nj / sqrt(*norm2_p) : 0.0;   // beta_{j-1} / ||u_{j-1}||,  beta_{j-1} = ||u_j||
+  const uint64_t n2 = n >> 1;
+  double acc = 0.0;
+  const double2* t2 = reinterpret_cast<const double2*>(t);
+  const double2* q2 = reinterpret_cast<const double2*>(uj);
+  const double2* p2 = reinterpret_cast<const double2*>(up);
+  double2* o2 = reinterpret_cast<double2*>(u_next);
+  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
+    const double2 tv = t2[i], qv = q2[i];
+    double2 v;
+    v.x = (tv.x - a * qv.x) * rj;
+    v.y = (tv.y - a * qv.y) * rj;
+    if (up) {
+      const double2 pv = p2[i];
+      v.x -= cp * pv.x;
+      v.y -= cp * pv.y;
+    }
+    o2[i] = v;
+    acc += v.x * v.x;
+    acc += v.y * v.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double v = (t[n - 1] - a * uj[n - 1]) * rj;
+    if (up) v -= cp * up[n - 1];
+    u_next[n - 1] = v;
+    acc += v * v;
+  }
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = acc;
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double tot = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) tot += __ldcg(partials + i);
+    tot = block_sum(tot, sm);
+    if (threadIdx.x == 0) {
+      *norm2_out = tot;
+      *beta_out = sqrt(tot);
+      *ticket = 0u;
+    }
+  }
+}
+// out[j] = coef[j] / sqrt(norm2[j]): multOut coefficients for an unnormalised basis
+__global__ void k_coef_scale(const double* __restrict__ coef, const double* __restrict__ norm2, uint32_t k, double* __restrict__ out) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < k) out[j] = coef[j] / sqrt(norm2[j]);
+}
+__global__ void k_div_sqrt(double* __restrict__ v, uint64_t n, const double* __restrict__ norm2) {
+  const double d = sqrt(*norm2);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) v[i] /= d;
 }
 
 // Index of local row l in the chunk-major gathered vector (see k_relabel in lz_graph.cu).
@@ -1034,7 +1107,7 @@ static lz_red make_red(const lz_ctx* c, unsigned long long seq) {
 }
 
 int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out, unsigned long long wait_seq,
-                  const double* push_src, unsigned long long red_seq) {
+                  const double* push_src, unsigned long long red_seq, const double* alpha_div) {
   const lz_red red = make_red(c, red_seq);
   for (uint32_t blk = 0; blk < c->ncolblk; blk++) {
     lz_push_job job;
@@ -1061,7 +1134,7 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
       auto kern = narrow ? k_spmv_sell<true> : k_spmv_sell<false>;
       kern<<<grid, kBlock, 0, c->stream>>>(c->sell_sp + (uint64_t)blk * c->n_items, c->sell_col, c->n_long, c->n_items,
                                            (uint32_t)c->n_loc, x_gather, q_local, w_out, c->partials, c->ticket + 0, alpha_out, acc, fin,
-                                           c->flags, blk, (uint32_t)c->world, wait_seq, job, group, red);
+                                           c->flags, blk, (uint32_t)c->world, wait_seq, job, group, red, alpha_div);
     } else {                                         // CSR: vector (sub-warp) per row by degree bin, or warp per row
       const lz_spmv_plan& plan = (c->spmv_variant == LZ_SPMV_WARP) ? c->plan_warp : c->plan_auto[blk];
       if (plan.nitems == 0) return lz_fail(LZ_ERR_ARG, "empty SpMV plan");
@@ -1069,7 +1142,7 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
       if (grid > plan.nitems) grid = plan.nitems;
       LZ_TRY(ensure_partials(c, grid));
       k_spmv_dot<<<grid, kBlock, 0, c->stream>>>(plan, c->seg[blk], c->seg[blk] + 1, c->col, x_gather, q_local, w_out, c->partials,
-                                                 c->ticket + 0, alpha_out, acc, fin, c->flags, blk, (uint32_t)c->world, wait_seq);
+                                                 c->ticket + 0, alpha_out, acc, fin, c->flags, blk, (uint32_t)c->world, wait_seq, alpha_div);
     }
     LZ_LAUNCH_CHECK();
   }
@@ -1083,6 +1156,26 @@ int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev
   LZ_TRY(ensure_partials(c, g));
   k_update_norm<<<g, kBlock, 0, c->stream>>>(w, qj, qprev, alpha, beta_prev, c->n_loc, c->partials, c->ticket + 1, norm2_out,
                                              make_red(c, red_seq), alpha);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+
+int lz_k_update_lagged(lz_ctx* c, const double* t, const double* uj, const double* uprev, const double* alpha, const double* norm2_j,
+                       const double* norm2_prev, double* u_next, double* norm2_out, double* beta_out) {
+  unsigned g = stream_grid(c, c->n_loc / 2 + 1);
+  LZ_TRY(ensure_partials(c, g));
+  k_update_lagged<<<g, kBlock, 0, c->stream>>>(t, uj, uprev, alpha, norm2_j, norm2_prev, c->n_loc, u_next, c->partials, c->ticket + 1,
+                                               norm2_out, beta_out);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+int lz_k_coef_scale(lz_ctx* c, const double* coef, const double* norm2, uint32_t k, double* out) {
+  k_coef_scale<<<(k + 127) / 128, 128, 0, c->stream>>>(coef, norm2, k, out);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+int lz_k_div_sqrt(lz_ctx* c, double* v, uint64_t n, const double* norm2) {
+  k_div_sqrt<<<stream_grid(c, n), kBlock, 0, c->stream>>>(v, n, norm2);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
