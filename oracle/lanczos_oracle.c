@@ -111,6 +111,7 @@ int lzo_tridiag_eig(uint32_t k, double* d, double* e_in, double* Z) {
     if (t > tst1) tst1 = t;
     int m = l;
     while (m < n) { if (fabs(e[m]) <= eps * tst1) break; m++; }
+    if (m >= n) m = n - 1;   /* only when e holds NaN (Lanczos breakdown upstream): e[n-1] = 0 stops the scan otherwise */
     if (m > l) {
       int iter = 0;
       do {

@@ -144,3 +144,69 @@ def test_live_reference_on_fresh_seed(lz, orc):
     np.testing.assert_allclose(beta, r["beta"], rtol=1e-13)
     assert rel2(ans, r["ans"]) < 1e-12
     assert np.array_equal(orc.top_k(ans), orc.top_k(r["ans"]))
+
+
+def _csr_from_dense(A):
+    n = A.shape[0]
+    ro = np.zeros(n + 1, dtype=np.uint32)
+    ro[1:] = np.cumsum((A != 0).sum(axis=1))
+    ci = np.concatenate([np.nonzero(A[i])[0] for i in range(n)]).astype(np.uint32)
+    return ro, ci
+
+
+def test_oracle_closed_forms(orc):
+    """Pins the restatement independently of the reference: graphs whose e^A x is known in closed form.
+    K_n and the star have 2 resp. 3 distinct eigenvalues, so Lanczos is exact after 2 resp. 3 steps for a generic x."""
+    rng = np.random.default_rng(11)
+    # complete graph: A = J - I  =>  e^A x = e^-1 (x + (e^n - 1)/n (1.x) 1)
+    n = 40
+    A = np.ones((n, n)) - np.eye(n)
+    ro, ci = _csr_from_dense(A)
+    x = 1.0 + rng.random(n)
+    y, alpha, beta = orc.expv(ro, ci, 2, x)
+    exact = np.exp(-1.0) * (x + (np.expm1(float(n)) / n) * x.sum())
+    assert rel2(y, exact) < 1e-12
+    # star: centre 0, eigenvalues +-sqrt(n-1) and 0
+    n = 50
+    A = np.zeros((n, n)); A[0, 1:] = 1; A[1:, 0] = 1
+    ro, ci = _csr_from_dense(A)
+    x = 1.0 + rng.random(n)
+    y, _, _ = orc.expv(ro, ci, 3, x)
+    w, V = np.linalg.eigh(A)
+    assert rel2(y, V @ (np.exp(w) * (V.T @ x))) < 1e-12
+    # cycle (circulant: e^A x by FFT, eigenvalues 2 cos(2 pi j / n)) and path (eigenvalues 2 cos(pi j / (n + 1)))
+    n = 64
+    A = np.zeros((n, n))
+    for i in range(n):
+        A[i, (i + 1) % n] = A[(i + 1) % n, i] = 1
+    ro, ci = _csr_from_dense(A)
+    x = rng.random(n)
+    y, _, _ = orc.expv(ro, ci, 30, x)
+    lam = 2.0 * np.cos(2.0 * np.pi * np.arange(n) / n)
+    exact = np.real(np.fft.ifft(np.exp(lam) * np.fft.fft(x)))
+    assert rel2(y, exact) < 1e-10
+    A[0, n - 1] = A[n - 1, 0] = 0                       # open the cycle: path
+    ro, ci = _csr_from_dense(A)
+    y, _, _ = orc.expv(ro, ci, 30, x)
+    j = np.arange(1, n + 1)
+    S = np.sqrt(2.0 / (n + 1)) * np.sin(np.pi * np.outer(j, j) / (n + 1))
+    exact = S @ (np.exp(2.0 * np.cos(np.pi * j / (n + 1))) * (S @ x))
+    assert rel2(y, exact) < 1e-10
+
+
+def test_oracle_regular_graph_with_nonconstant_x(orc):
+    """d-regular graph: with x = ones the reference breaks down (beta_0 = 0, NaN); a non-constant x must work and agree with
+    the dense eigendecomposition. Circulant 4-regular graph on 101 vertices."""
+    n = 101
+    A = np.zeros((n, n))
+    for i in range(n):
+        for s in (1, 7):
+            A[i, (i + s) % n] = A[(i + s) % n, i] = 1
+    ro, ci = _csr_from_dense(A)
+    assert np.all(np.diff(ro) == 4)
+    x = 1.0 + np.random.default_rng(3).random(n)
+    y, _, _ = orc.expv(ro, ci, 35, x)
+    w, V = np.linalg.eigh(A)
+    assert rel2(y, V @ (np.exp(w) * (V.T @ x))) < 1e-10
+    y1, _, _ = orc.expv(ro, ci, 5, np.ones(n))          # the documented breakdown: not finite, and not silently "fixed"
+    assert not np.all(np.isfinite(y1))
