@@ -106,35 +106,92 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload):
-    """dram bytes per SpMV launch from the committed ncu --set full capture of this workload, if there is one."""
+def ncu_traffic(workload, world):
+    """dram bytes per SpMV launch from a committed ncu --set full capture of exactly this (workload, GPU count); else None."""
     p = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(workload)
+            return json.load(open(p)).get(f"{workload}@{world}")
         except Exception:
             return None
     return None
 
 
+def workload_config(w, n, nnz, k, world):
+    """The `config` object — identical in the `ours` and `reference` arms (same workload, same keys)."""
+    n_loc, nnz_loc = n / world, nnz / world
+    return {"workload": w["name"], "n": n, "nnz": nnz, "k": k, "reorth": "none", "x": "ones",
+            "l2_policy": "inputs larger than L2 (CSR %.2f GB + basis %.2f GB per GPU)" % ((4.0 * nnz_loc + 4 * n_loc) / 1e9, 8.0 * n_loc * k / 1e9)}
+
+
+def summary_fixture(w, scale_override, k):
+    """Committed summary of the reference's (or, for sizes the CPU reference cannot reach, this library's 1-GPU) answer."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fixture_parity as fp
+    if w["kind"] != "rmat":
+        return fp, None
+    scale = scale_override or w["scale"]
+    path = fp.fixture_path("rmat", scale, k, w["seed"], w["ef"])
+    if path is None:
+        own = os.path.join(fp.GOLDEN, f"own_rmat_s{scale}_k{k}_summary.npz")
+        path = own if os.path.exists(own) else None
+    return fp, path
+
+
 def cpu_reference_sample(orc, csr_path, n, nnz, iters, reps=1):
-    """Times the reference's own CPU Lanczos (oracle/_ref/ref_final = lanczosDecomp<double>(A, iters, ones, cuda=false),
-    parallel-final/lib/lanczos.cu:17-60, single-threaded) on `iters` steps of the workload graph. Falls back to the C
-    restatement (oracle/lanczos_oracle.c) when the compiled reference is not there."""
+    """Times the reference's own CPU pipeline (oracle/_ref/ref_final: lanczosDecomp<double>(A, m, ones, cuda=false) ->
+    eigenDecomp -> multOut, parallel-final/main.cu:83-93; Lanczos single-threaded, multOut on the reference's 4 OpenBLAS
+    threads) at Krylov dimension m = `iters` on the workload graph: a bounded sample of the k-step job with every stage present.
+    Returns per-repetition iterations/s, seconds, the kind, and the reference's alpha/beta of the sample (the leading
+    coefficients of the full run). Falls back to the C restatement (oracle/lanczos_oracle.c) when oracle/_ref is absent."""
     if orc.have_ref():
-        r = orc.run_ref_final(None, None, iters, iters=iters, reps=reps, want_output=False, csr_path=csr_path)
-        vals = [t["iters_per_s"] for t in r["timings"]]
-        secs = [t["lanczos_s"] for t in r["timings"]]
-        return vals, secs, "reference"
-    lz = graft.load_package()
-    _, ro, ci = lz.read_bin(csr_path)
-    vals, secs = [], []
+        r = orc.run_ref_final(None, None, iters, reps=reps, want_output=True, csr_path=csr_path)
+        secs = [t["total_s"] for t in r["timings"]]
+        vals = [iters / s for s in secs]
+        return vals, secs, "reference", r["alpha"], r["beta"]
+    with open(csr_path, "rb") as f:                      # LZCSR1 cache, read without the product library
+        assert f.read(8) == b"LZCSR1\0\0"
+        nn, mm = (int(v) for v in np.fromfile(f, np.uint64, 2))
+        ro, ci = np.fromfile(f, np.uint32, nn + 1), np.fromfile(f, np.uint32, mm)
+    vals, secs, a, b = [], [], None, None
     for _ in range(reps):
         t0 = time.perf_counter()
-        orc.lanczos(ro, ci, iters, np.ones(n))
+        _, a, b = orc.expv(ro, ci, iters, np.ones(n))
         dt = time.perf_counter() - t0
         vals.append(iters / dt); secs.append(dt)
-    return vals, secs, "port"
+    return vals, secs, "port", a, b
+
+
+_MAKE_CSR = """
+import sys
+sys.path.insert(0, sys.argv[1])
+import __graft_entry__ as g
+lz = g.load_package()
+kind, a, b, seed, path, dev = sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6], int(sys.argv[7])
+spec = {"rmat": lambda: lz.GraphSpec.rmat(a, b, seed), "er": lambda: lz.GraphSpec.er(a, b, seed), "band": lambda: lz.GraphSpec.band(a, seed)}[kind]()
+try:
+    with lz.Context(dev) as ctx:
+        ctx.graph_generate(spec)
+        ro, ci = ctx.csr_download()
+except lz.LzError:
+    _, ro, ci = lz.generate_host(spec)
+lz.write_bin(path, ro, ci)
+print(len(ro) - 1, int(ro[-1]))
+"""
+
+
+def make_csr_file(w, scale_override, n_override, path, device):
+    """Writes the workload's CSR cache in a SEPARATE process, so the process that times the reference never loads liblzb200.so."""
+    if w["kind"] == "rmat":
+        a, b = scale_override or w["scale"], w["ef"]
+    elif w["kind"] == "er":
+        a, b = n_override or w["n"], w["m"]
+    else:
+        a, b = n_override or w["n"], 0
+    r = subprocess.run([sys.executable, "-c", _MAKE_CSR, ROOT, w["kind"], str(a), str(b), str(w["seed"]), path, str(device)],
+                       check=True, capture_output=True, text=True)
+    n, nnz = (int(v) for v in r.stdout.split()[-2:])
+    return n, nnz
 
 
 def sample_iters_for(nnz):
@@ -155,6 +212,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reorth-detail", action="store_true")
+    ap.add_argument("--save-summary", default=None, help="write a summary fixture (.npz) of this run's answer (rank 0)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -169,39 +227,40 @@ def main():
         w["name"] += " [override: " + ", ".join(overrides) + "]"
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
-    lz = graft.load_package()
-
     # ---------------------------------------------------------------------------------------------- reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
         orc = graft.load_oracle()              # the oracle is only ever loaded for the reference / cpu_baseline legs
-        spec = make_spec(lz, w, args.scale, args.n)
-        csr_path = os.path.join(tempfile.gettempdir(), f"lz_bench_{args.workload}_{args.scale or ''}.bin")
-        try:
-            with lz.Context(local_rank) as ctx:           # input construction only (not timed, not on the measured path)
-                ctx.graph_generate(spec)
-                ro, ci = ctx.csr_download()
-        except lz.LzError:
-            _, ro, ci = lz.generate_host(spec)
-        n, nnz = len(ro) - 1, int(ro[-1])
-        lz.write_bin(csr_path, ro, ci)
-        del ro, ci
+        csr_path = os.path.join(tempfile.gettempdir(), f"lz_bench_{args.workload}_{args.scale or ''}_{os.getpid()}.bin")
+        n, nnz = make_csr_file(w, args.scale, args.n, csr_path, local_rank)     # input construction: separate process, untimed
         m = sample_iters_for(nnz)
         total = args.steps + args.warmup
-        vals, secs, kind = cpu_reference_sample(orc, csr_path, n, nnz, m, reps=total)
+        vals, secs, kind, a_ref, b_ref = cpu_reference_sample(orc, csr_path, n, nnz, m, reps=total)
         os.unlink(csr_path)
         vals, secs = vals[args.warmup:], secs[args.warmup:]
         value = m * len(secs) / sum(secs)
-        sample = f"{m} Lanczos steps of {w['name']} per step (lanczosDecomp<double>(A,{m},ones,cuda=false)), 1 thread"
+        sample = (f"per step: the reference pipeline at Krylov dimension {m} on {w['name']} (lanczosDecomp<double>(A,{m},ones,cuda=false) -> "
+                  f"eigenDecomp -> multOut; Lanczos on 1 thread, multOut on the reference's 4 OpenBLAS threads)")
+        lead = {"alpha": [float(v) for v in a_ref[:m]], "beta": [float(v) for v in b_ref[:m - 1]]}
+        fp, fix = summary_fixture(w, args.scale, k)
+        if fix and "own_" not in os.path.basename(fix):       # the sample's coefficients are the leading ones of the committed k-step reference run
+            g = np.load(fix)
+            lead["max_rel_diff_vs_fixture"] = float(max(np.max(np.abs(a_ref[:m] - g["alpha"][:m]) / np.abs(g["alpha"][:m])),
+                                                         np.max(np.abs(b_ref[:m - 1] - g["beta"][:m - 1]) / np.abs(g["beta"][:m - 1]))))
+            lead["fixture"] = os.path.basename(fix)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w["name"], "n": n, "nnz": nnz, "k": k, "reorth": "none", "sample_iters": m},
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
-                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "config": workload_config(w, n, nnz, k, args.gpus),
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "sample_iters": m,
+                                 "host_cores_available": os.cpu_count()},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "tridiag_lead": lead}
         print(json.dumps(line), flush=True)
         return 0
+
+    lz = graft.load_package()
 
     # ------------------------------------------------------------------------------------------------------ our arm
     import torch
@@ -290,7 +349,7 @@ def main():
     spmv_gbs = b_spmv / (tm.spmv_ms_avg * 1e-3) / 1e9 if tm.spmv_ms_avg else None
     spmv_kernel = "k_spmv_sell" if os.environ.get("LZ_SPMV_VARIANT", "0") in ("", "0") else "k_spmv_dot"
     roofline = {"bound": "hbm", "kernel": spmv_kernel, "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
-                "frac": (spmv_gbs / peak) if spmv_gbs else None, "traffic": ncu_traffic(args.workload),
+                "frac": (spmv_gbs / peak) if spmv_gbs else None, "traffic": ncu_traffic(args.workload, world),
                 "algorithmic_bytes_per_launch": b_spmv, "peak_source": peak_src,
                 # what actually binds this kernel on a random graph: the SM load path's line-lookup rate
                 "gather": {"achieved_ggathers_s": gi.nnz_local / (tm.spmv_ms_avg * 1e-3) / 1e9 if tm.spmv_ms_avg else None,
@@ -302,19 +361,26 @@ def main():
     b_mult = 8.0 * gi.n_local * k + 8.0 * gi.n_local
     detail["multout_gbs"] = b_mult / (tm.multout_ms * 1e-3) / 1e9 if tm.multout_ms else None
 
-    # the config's full-reorthogonalisation variant (C3), reported next to the headline
+    # the config's full-reorthogonalisation variant (BASELINE configs[2] "with full reorthogonalisation"): its own top-level
+    # object with its own roofline (the Gram-Schmidt passes over the resident basis are HBM-bound GEMV-T + GEMV-N)
+    reorth_variant = None
     if w.get("reorth") and not args.no_reorth_detail:
         ctx.lanczos_run(k, lz.REORTH_FULL); ctx.sync()
         barrier()
         ctx.timer_start()
-        ctx.lanczos_run(k, lz.REORTH_FULL)
-        ms_r = max_over_ranks(ctx.timer_stop())
+        for _ in range(3):
+            ctx.lanczos_run(k, lz.REORTH_FULL)
+        ms_r = max_over_ranks(ctx.timer_stop()) / 3.0
         second = ctx.timings().reorth_second_passes
         # one classical Gram-Schmidt pass per step (8n*k(k+1) + 16nk), plus the repeated passes
         b_reorth = (8.0 * gi.n_local * k * (k + 1) + 16.0 * gi.n_local * k) * (1.0 + second / max(k - 1, 1))
-        detail["full_reorth"] = {"lanczos_ms": ms_r, "iters_per_s": k / (ms_r * 1e-3), "scheme": "CGS every step, second pass when ||w'||^2 < ||w||^2 / 2 (DGKS)", "second_passes": second,
-                                 "reorth_algorithmic_gb": b_reorth / 1e9,
-                                 "reorth_gbs": b_reorth / max((ms_r - tm.lanczos_ms) * 1e-3, 1e-9) / 1e9}
+        r_gbs = b_reorth / max((ms_r - tm.lanczos_ms) * 1e-3, 1e-9) / 1e9
+        reorth_variant = {"metric": METRIC, "value": k / (ms_r * 1e-3), "unit": UNIT, "lanczos_ms": ms_r, "reorth": "full",
+                          "scheme": "CGS every step, second pass when ||w'||^2 < ||w||^2 / 2 (DGKS)", "second_passes": second,
+                          "roofline": {"bound": "hbm", "kernel": "k_multidot + k_combine", "achieved": r_gbs, "peak": peak, "unit": "GB/s",
+                                       "frac": r_gbs / peak, "algorithmic_bytes": b_reorth,
+                                       "note": "reorthogonalisation bytes over (reorth run - plain run) device time"}}
+        detail["full_reorth"] = {"lanczos_ms": ms_r, "iters_per_s": k / (ms_r * 1e-3), "reorth_gbs": r_gbs}
 
     # end to end through the reference-facing call with HOST buffers (pinned), H2D of x and D2H of the answer inside
     x_host = torch.ones(n, dtype=torch.float64).pin_memory().numpy()
@@ -338,37 +404,73 @@ def main():
            "call": "lz_expv_host (pinned host x -> pinned host e^A x)" if world == 1 else
                    "lz_expv_host_root (rank 0: pinned host x -> NVLink broadcast -> ... -> pinned host e^A x)"}
     finite = bool(np.isfinite(y_host).all()) if want else True
+    alpha_g, beta_g = ctx.get_tridiag()
 
-    # CPU baseline: the reference's own serial Lanczos on the same graph, bounded sample, rank 0, N == 1 only
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        orc = graft.load_oracle()
-        csr_path = os.path.join(tempfile.gettempdir(), f"lz_bench_{args.workload}_{os.getpid()}.bin")
-        ro, ci = ctx.csr_download()
-        lz.write_bin(csr_path, ro, ci)
-        del ro, ci
-        m = sample_iters_for(nnz)
-        vals, secs, kind = cpu_reference_sample(orc, csr_path, n, nnz, m, reps=1)
-        os.unlink(csr_path)
-        cpu = {"value": vals[0], "unit": UNIT, "cores": 1, "kind": kind,
-               "sample": f"{m} Lanczos steps of {w['name']} (reference lanczosDecomp<double>, cuda=false, single thread), {secs[0]:.1f} s",
-               "host_cores_available": os.cpu_count()}
+    # end to end when the caller wants the RANKING (BASELINE configs[1]: "e^A x + centrality ranking"): host x in, the 100 most
+    # central vertices out — lz_top_k selects on the device, so 100 (id, value) pairs cross PCIe instead of n doubles
+    def e2e_rank_call():
+        ctx.set_start_vector_root(x_host if want else None, 0) if world > 1 else ctx.set_start_vector(x_host)
+        ctx.lanczos_run(k); ctx.tridiag_expv(); ctx.multout()
+        return ctx.top_k(100)
+    for _ in range(2):
+        top_idx, top_val = e2e_rank_call()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        top_idx, top_val = e2e_rank_call()
+    rank_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_rank = {"value": k * args.steps / rank_s, "unit": UNIT, "ms_per_step": 1e3 * rank_s / args.steps, "h2d_bytes_per_step": 8 * n,
+                "d2h_bytes_per_step": 100 * 12, "call": "lz_set_start_vector(host x) + lz_lanczos_run + lz_tridiag_expv + lz_multout + lz_top_k(100)"}
+
+    # parity of THIS run's answer (the vector the e2e call returned to rank 0) against the committed summary of the reference
+    parity = None
+    fp, fix = summary_fixture(w, args.scale, k)
+    if rank == 0:
+        if fix:
+            parity = fp.compare(y_host, fix, alpha_g, beta_g, top_idx, top_val)
+            if "own_" in os.path.basename(fix):
+                parity["source"] = "this library's 1-GPU answer (the CPU reference cannot reach this size); " + parity["source"]
+        else:
+            parity = {"fixture": None, "note": "no committed reference summary for this workload; see tests/ for its parity cases",
+                      "top_k_api_identical_to_host_argsort": bool(np.array_equal(fp.top_order(y_host, 100), top_idx))}
+        if args.save_summary:
+            sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+            import make_golden_c3 as mg
+            meta = {"graph": {k_: w[k_] for k_ in ("kind", "scale", "ef", "seed") if k_ in w}, "k": k, "x": "ones", "nnz": nnz,
+                    "source": f"bench.py --save-summary on {world} GPU(s), liblzb200 (NOT the reference)"}
+            np.savez_compressed(args.save_summary, **mg.summarize(np.array(y_host), alpha_g, beta_g, meta))
+
     xmode, xfrac = ctx.exchange_info()
     exchange = {0: "none (one GPU)", 1: "ncclAllGather", 2: "peer stores over NVLink, whole vector",
                 3: "peer stores over NVLink, referenced entries only (%.3g of the vector)" % xfrac}[xmode]
     ctx.close()
 
+    # CPU baseline: the reference's own pipeline on the same graph, bounded sample, rank 0, N == 1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        orc = graft.load_oracle()
+        csr_path = os.path.join(tempfile.gettempdir(), f"lz_bench_{args.workload}_{os.getpid()}.bin")
+        make_csr_file(w, args.scale, args.n, csr_path, local_rank)
+        m = sample_iters_for(nnz)
+        vals, secs, kind, a_ref, b_ref = cpu_reference_sample(orc, csr_path, n, nnz, m, reps=1)
+        os.unlink(csr_path)
+        cpu = {"value": vals[0], "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"the reference pipeline at Krylov dimension {m} on {w['name']} (lanczosDecomp<double>, cuda=false, 1 thread; "
+                         f"eigenDecomp; multOut on 4 OpenBLAS threads), {secs[0]:.1f} s",
+               "host_cores_available": os.cpu_count(),
+               # the reference's coefficients from this very run vs the GPU run's (same graph, same start vector)
+               "tridiag_lead_max_rel_diff_vs_gpu": float(max(np.max(np.abs(a_ref[:m] - alpha_g[:m]) / np.abs(a_ref[:m])),
+                                                             np.max(np.abs(b_ref[:m - 1] - beta_g[:m - 1]) / np.abs(b_ref[:m - 1])))) if m > 1 else None}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w["name"], "n": n, "nnz": nnz, "k": k, "reorth": "none", "x": "ones",
-                           "l2_policy": "inputs larger than L2 (CSR %.2f GB + basis %.2f GB per GPU)" % (
-                               (4.0 * gi.nnz_local + 4 * gi.n_local) / 1e9, 8.0 * gi.n_local * k / 1e9),
-                           "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU", "exchange": exchange,
-                           "launch": "CUDA graph replay of the k-step loop" if graph_replay else "stream launches"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "result_finite": finite, "detail": detail}
+                "config": workload_config(w, n, nnz, k, world),
+                "impl_config": {"parallelism": f"row-sharded x{world}" if world > 1 else "single GPU", "exchange": exchange,
+                                "launch": "CUDA graph replay of the k-step loop" if graph_replay else "stream launches"},
+                "clocks": clocks, "e2e": e2e, "e2e_rank": e2e_rank, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "parity": parity, "result_finite": finite, "reorth_variant": reorth_variant, "detail": detail}
         print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()

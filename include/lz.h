@@ -139,6 +139,13 @@ int lz_multout(lz_ctx* ctx);
 /* ans (n doubles, original order) to the host (cublasGetVector, cu_multiplyOut.cu:77). Synchronises. With world > 1 the call
  * is collective; a rank that does not need the vector may pass NULL (it still takes part in the gather). */
 int lz_get_ans(lz_ctx* ctx, double* ans_host);
+/* Centrality ranking: the m (<= 1024) largest entries of the last lz_multout result, descending, ties towards the lower
+ * vertex id (argsort(-y) with a stable index tie-break) — ORIGINAL vertex ids and their values. Selected
+ * on the device (radix select + one small sort), so the caller downloads m pairs instead of n doubles. The reference only
+ * prints the vector (parallel-final/lib/write_ans.h:10-16); BASELINE.json names the top-100 ranking as an output of the path.
+ * *count_out (optional) = min(m, n) valid pairs. Synchronises. With world > 1 the call is collective and every rank receives the
+ * same result (idx_out / val_out may be NULL on ranks that do not need it). */
+int lz_top_k(lz_ctx* ctx, uint32_t m, uint32_t* idx_out, double* val_out, uint32_t* count_out);
 /* Whole pipeline with HOST buffers, what lanczosDecomp<double>(A,k,x,true) + eigenDecomp + multOut do in main.cu:115-127:
  * H2D x, k steps, eigensolve, multOut, D2H ans. */
 int lz_expv_host(lz_ctx* ctx, const double* x_host, uint32_t k, int reorth, double* ans_host);

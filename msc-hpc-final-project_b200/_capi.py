@@ -97,6 +97,7 @@ _sig("lz_estimate_change", _ctx, C.c_uint32, _P(C.c_double))
 _sig("lz_choose_k", _ctx, C.c_double, _P(C.c_uint32), _P(C.c_double))
 _sig("lz_multout", _ctx)
 _sig("lz_get_ans", _ctx, _f64p)
+_sig("lz_top_k", _ctx, C.c_uint32, _u32p, _f64p, _u32p)
 _sig("lz_expv_host", _ctx, _f64p, C.c_uint32, C.c_int, _f64p)
 _sig("lz_expv_host_root", _ctx, _f64p, C.c_uint32, C.c_int, _f64p, C.c_int)
 _sig("lz_set_start_vector_root", _ctx, _f64p, C.c_int)
@@ -248,6 +249,11 @@ class Context:
             assert x.shape == (self.graph_info().n,)
             _check(lib.lz_set_start_vector(self._h, _f64(x)))
 
+    def set_start_vector_root(self, x, root=0):
+        """Collective: only `root` passes x (one PCIe upload); the other ranks pass None and receive it over NVLink."""
+        xp = None if x is None else _f64(np.ascontiguousarray(x, np.float64))
+        _check(lib.lz_set_start_vector_root(self._h, xp, root))
+
     def lanczos_run(self, k, reorth=REORTH_NONE):
         _check(lib.lz_lanczos_run(self._h, k, reorth))
         self._k = k
@@ -285,6 +291,12 @@ class Context:
         y = np.empty(n) if out is None else out
         _check(lib.lz_get_ans(self._h, _f64(y)))
         return y
+
+    def top_k(self, m=100):
+        """(idx, val): the m largest entries of the last multout result, descending, ties -> lower vertex id."""
+        idx, val, cnt = np.empty(m, np.uint32), np.empty(m), C.c_uint32(0)
+        _check(lib.lz_top_k(self._h, m, _u32(idx), _f64(val), C.byref(cnt)))
+        return idx[:cnt.value], val[:cnt.value]
 
     def expv_host(self, x, k, reorth=REORTH_NONE, out=None, want_result=True):
         """want_result=False (world > 1 only): this rank takes part but does not copy e^A x to its host."""

@@ -366,6 +366,7 @@ extern "C" int lz_destroy(lz_ctx* c) {
   drop_graph(c);
   free_vectors(c);
   lz_free_graph(c);
+  lz_free_rank(c);
   cudaFree(c->scal); cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->status); cudaFree(c->flush_buf);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : {c->ev_a, c->ev_b, c->ev_e0, c->ev_e1, c->ev_m0, c->ev_m1, c->ev_t0, c->ev_t1})

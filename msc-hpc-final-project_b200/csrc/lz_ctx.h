@@ -163,6 +163,14 @@ struct lz_ctx {
   double* graph_V = nullptr;
   uint64_t graph_epoch = 0, epoch = 0;   // epoch: bumped whenever the graph data or the vectors are re-created
 
+  // ---- ranking (lz_rank.cu) -------------------------------------------------------------------------------------------
+  void* rank_state = nullptr;              // device, radix-select state
+  unsigned long long* rank_key = nullptr;  // device, [rank_cap] candidate keys (m per rank)
+  uint32_t* rank_idx = nullptr;            // device, [rank_cap] candidate original vertex ids
+  uint32_t* rank_out_idx = nullptr;        // device, sorted result
+  double* rank_out_val = nullptr;
+  uint32_t rank_cap = 0;
+
   // ---- measurement ------------------------------------------------------------------------------------------------
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -175,6 +183,8 @@ struct lz_ctx {
 int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, uint32_t* ci_d);  // takes ownership of ro_d / ci_d
 void lz_free_graph(lz_ctx* c);
 int lz_build_push_lists(lz_ctx* c);   // collective; call after the peers are mapped
+// lz_rank.cu
+void lz_free_rank(lz_ctx* c);
 
 // lz_kernels.cu — all launches are asynchronous on c->stream
 int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, double* w_out, double* alpha_out /* device scalar or null */,

@@ -79,6 +79,16 @@ class lanczosDecomp {
   const T* get_beta() const { return beta; }
   const T* get_ans_ptr() const { return ans; }
   void get_basis(unsigned j, T* out) const;
+  // Centrality ranking (valid after multOut): the m largest entries of e^A x, descending, ties -> lower vertex id. Selected on
+  // the device (lz_top_k); returns the number of pairs written. The reference has no ranking call — its users sort write_ans output.
+  unsigned top_k(unsigned m, unsigned* idx_out, T* val_out) const {
+    std::vector<double> v(m);
+    uint32_t cnt = 0;
+    static_assert(sizeof(unsigned) == sizeof(uint32_t), "32-bit vertex ids");
+    if (lz_top_k(ctx, m, reinterpret_cast<uint32_t*>(idx_out), v.data(), &cnt) != LZ_OK) fail("lanczosDecomp: lz_top_k");
+    for (unsigned i = 0; i < cnt; i++) val_out[i] = (T)v[i];
+    return cnt;
+  }
   lz_timings timings() const { lz_timings t{}; lz_timings_get(ctx, &t); return t; }
 
   friend class eigenDecomp<T>;

@@ -7,7 +7,7 @@
 //   ./final -k 30 --graph ba -n 100000 -b 20                      Barabasi-Albert, as main.cu:67-71
 //   options: --reorth (full reorthogonalisation)  --gpus N (row-sharded, one host thread per GPU, NCCL)
 //            --check FILE (raw float64 e^A x to compare with, e.g. written by oracle/_ref/ref_final --out)
-//            --write FILE (one value per line, write_ans)
+//            --write FILE (one value per line, write_ans)   --top M (print the M most central vertices, device-side ranking)
 //
 // Same object sequence as the reference: adjMatrix -> lanczosDecomp<double>(A,k,x,cuda=true) -> eigenDecomp<double> ->
 // multOut(L,E,A,true), same TIMING / ERROR CHECKING tables. The reference's serial arm (main.cu:83-99) is not here: this
@@ -81,6 +81,7 @@ int main(int argc, char** argv) {
   unsigned scale = 16, ef = 8;
   uint64_t seed = 1;
   int reorth = LZ_REORTH_NONE, gpus = 1;
+  unsigned top = 0;
 
   // long options first; what is left goes to the reference's getopt string
   std::vector<char*> rest{argv[0]};
@@ -96,6 +97,7 @@ int main(int argc, char** argv) {
     else if (a == "--write") write_file = val();
     else if (a == "--gpus") gpus = atoi(val());
     else if (a == "--reorth") reorth = LZ_REORTH_FULL;
+    else if (a == "--top") top = (unsigned)atoi(val());
     else rest.push_back(argv[i]);
   }
   if (parseArguments((int)rest.size(), rest.data(), filename, krylov_dim, verbose, n, deg, edges) != 0) return 2;
@@ -157,6 +159,14 @@ int main(int argc, char** argv) {
     tm = cu_L.timings();
     result.assign(cu_L.get_ans_ptr(), cu_L.get_ans_ptr() + n);
     if (!write_file.empty()) write_ans(write_file, cu_L);                             // main.cu:159
+    if (top) {
+      std::vector<unsigned> ti(top);
+      std::vector<double> tv(top);
+      const unsigned cnt = cu_L.top_k(top, ti.data(), tv.data());
+      std::cout << "TOP " << cnt << " vertices by total communicability (rank vertex value)\n" << std::setprecision(17);
+      for (unsigned i = 0; i < cnt; i++) std::cout << "rank " << i + 1 << ' ' << ti[i] << ' ' << tv[i] << '\n';
+      std::cout << std::setprecision(6);
+    }
   }
 
   std::cout << std::setfill('~') << std::setw(WIDTH) << '\n' << std::setfill(' ');

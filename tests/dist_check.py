@@ -39,6 +39,9 @@ def main():
             print(f"[rank {rank}] {name} expv done rel={rel2(y, gl['ans']):.2e}", flush=True)
         assert rel2(y, gl["ans"]) < 1e-9, (name, rel2(y, gl["ans"]))
         assert np.array_equal(orc.top_k(y), orc.top_k(gl["ans"])), name
+        for m in (1, 100, 1024):                       # ranking through the product API: per-rank radix select + all-gather + merge
+            idx, val = ctx.top_k(m)
+            assert np.array_equal(idx, orc.top_k(y, m)) and np.array_equal(val, y[idx]), (name, m)
         y2 = ctx.expv_host(gl["x_random"], k)
         assert rel2(y2, gl["ans_random"]) < 1e-9, name
         yr = ctx.expv_host(None, k, lz.REORTH_FULL)
@@ -99,6 +102,18 @@ def main():
     assert ctx.exchange_info()[0] == lz.EXCHANGE_PEER_DENSE
     ref, _, _ = orc.expv(ro, ci, 30, np.ones(n))
     assert rel2(y, ref) < 1e-9 and np.array_equal(orc.top_k(y), orc.top_k(ref))
+    assert np.array_equal(ctx.top_k(100)[0], orc.top_k(ref))
+    # BASELINE configs[1] (R-MAT 2^20, k=30) on `world` GPUs against the committed summary of the reference's answer
+    import fixture_parity as fp
+    ctx.graph_generate(lz.GraphSpec.rmat(20, 8, 1))
+    for reorth in (lz.REORTH_NONE, lz.REORTH_FULL):
+        y20 = ctx.expv_host(None, 30, reorth)
+        a20, b20 = ctx.get_tridiag()
+        i20, v20 = ctx.top_k(100)
+        r = fp.compare(y20, fp.fixture_path("rmat", 20, 30), a20, b20, i20, v20)
+        assert r["ok"] and r["alpha_lead_rel"] < 1e-8 and r["beta_lead_rel"] < 1e-8, r
+    ctx.graph_generate(spec)
+    assert np.array_equal(ctx.expv_host(None, 30), y)                  # back on the previous graph: same bits as before
     # single-caller entry point: only rank 0 passes x and receives the answer
     xr = np.random.default_rng(9).random(n)
     yr_all = ctx.expv_host(xr, 30)

@@ -117,3 +117,41 @@ def test_shard_layout_arithmetic(n, world):
     for r in range(world):
         mine = np.sort(new[new // n_loc == r]) - r * n_loc
         assert np.array_equal(mine, np.arange(len(mine)))
+
+
+def test_fixture_parity_checker_against_oracle_ranking(orc, golden):
+    """tests/fixture_parity.py (the checker bench.py uses for its `parity` object): its host ranking equals the oracle's on
+    vectors with ties, and a summary made from a vector compares clean with that vector and dirty with a perturbed one."""
+    import fixture_parity as fp
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_c3 as mg
+    rng = np.random.default_rng(0)
+    y = np.floor(rng.random(5000) * 50.0)                      # many ties
+    for m in (1, 10, 100, 5000):
+        assert np.array_equal(fp.top_order(y, m), orc.top_k(y, m))
+    g = golden("c1_er_n10000_k20")
+    y = g["ans"]
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "s.npz")
+        np.savez_compressed(path, **mg.summarize(y, g["alpha"], g["beta"], {"source": "test"}))
+        r = fp.compare(y, path, g["alpha"], g["beta"], orc.top_k(y, 100), y[orc.top_k(y, 100)])
+        assert r["ok"] and r["rel_2norm"] == 0.0 and r["top_k_api_identical"] and r["alpha_lead_rel"] == 0.0
+        y2 = y.copy()
+        y2[int(g["n"]) // 2] *= 1.0 + 1e-6                    # one wrong entry anywhere must show up (block sums cover every entry)
+        assert not fp.compare(y2, path)["ok"]
+        y3 = y.copy()
+        t = orc.top_k(y, 2)
+        y3[t[0]], y3[t[1]] = y[t[1]], y[t[0]]                 # swapped ranking
+        assert not fp.compare(y3, path)["top100_identical"]
+
+
+def test_c3_and_c2_reference_summaries_are_committed():
+    import fixture_parity as fp
+    for scale, k in ((20, 30), (24, 50)):
+        p = fp.fixture_path("rmat", scale, k)
+        assert p, (scale, k)
+        g = np.load(p)
+        assert len(g["alpha"]) == k and len(g["beta"]) == k - 1 and int(g["n"]) == 1 << scale
+        assert float(g["top_gap"]) > 1e-6 and "ref_final" in str(g["meta"])
