@@ -14,30 +14,39 @@
 #include <string.h>
 #include <unistd.h>
 
+namespace {
+struct NcclBinding {
+  lz_nccl_api api{};
+  bool ok = false;
+  char err[256] = "";
+  NcclBinding() {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // share a copy that is already in the process
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) { snprintf(err, sizeof(err), "libnccl.so.2 could not be loaded: %s", dlerror()); return; }
+    bool all = true;
+    auto sym = [&](const char* name) { void* p = dlsym(h, name); if (!p) all = false; return p; };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.CommAbort = (decltype(api.CommAbort))sym("ncclCommAbort");
+    api.CommSplit = (decltype(api.CommSplit))dlsym(h, "ncclCommSplit");   // optional
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+    if (!all) { snprintf(err, sizeof(err), "libnccl.so.2 lacks a required symbol"); return; }
+    ok = true;
+  }
+};
+}  // namespace
+// One host thread per GPU in one process is a supported mode (lib/final.cc run_multi): the binding is a function-local
+// static, whose initialisation C++11 makes thread-safe.
 const lz_nccl_api* lz_nccl() {
-  static lz_nccl_api api;
-  static int state = 0;   // 0 untried, 1 ok, -1 failed
-  if (state == 1) return &api;
-  if (state == -1) { lz_fail(LZ_ERR_NCCL, "libnccl.so.2 could not be loaded"); return nullptr; }
-  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // share a copy that is already in the process
-  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
-  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
-  if (!h) { state = -1; lz_fail(LZ_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror()); return nullptr; }
-  bool ok = true;
-  auto sym = [&](const char* name) { void* p = dlsym(h, name); if (!p) ok = false; return p; };
-  api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
-  api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
-  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
-  api.CommAbort = (decltype(api.CommAbort))sym("ncclCommAbort");
-  api.CommSplit = (decltype(api.CommSplit))dlsym(h, "ncclCommSplit");   // optional
-  api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
-  api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
-  api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
-  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
-  api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
-  if (!ok) { state = -1; lz_fail(LZ_ERR_NCCL, "libnccl.so.2 lacks a required symbol"); return nullptr; }
-  state = 1;
-  return &api;
+  static const NcclBinding binding;
+  if (!binding.ok) { lz_fail(LZ_ERR_NCCL, "%s", binding.err); return nullptr; }
+  return &binding.api;
 }
 
 static void drop_graph(lz_ctx* c) {
@@ -108,8 +117,9 @@ int setup_peers(lz_ctx* c) {
   mine.device = c->device;
   mine.ok = want && cudaIpcGetMemHandle(&mine.hx, c->xfull) == cudaSuccess && cudaIpcGetMemHandle(&mine.hf, c->flags) == cudaSuccess;
   cudaGetLastError();
-  lz_xchg* dbuf = nullptr;
-  LZ_CUDA(cudaMalloc((void**)&dbuf, sizeof(lz_xchg) * W));
+  struct DBuf { lz_xchg* p = nullptr; ~DBuf() { cudaFree(p); } } dguard;
+  LZ_CUDA(cudaMalloc((void**)&dguard.p, sizeof(lz_xchg) * W));
+  lz_xchg* dbuf = dguard.p;
   LZ_CUDA(cudaMemcpyAsync(dbuf + c->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
   LZ_NCCL(lz_nccl()->AllGather(dbuf + c->rank, dbuf, sizeof(lz_xchg), ncclChar, c->comm, c->stream));
   LZ_CUDA(cudaMemcpyAsync(all.data(), dbuf, sizeof(lz_xchg) * W, cudaMemcpyDeviceToHost, c->stream));
@@ -144,7 +154,6 @@ int setup_peers(lz_ctx* c) {
   LZ_NCCL(lz_nccl()->AllReduce(flag_d, flag_d, 1, ncclDouble, ncclMin, c->comm, c->stream));
   LZ_CUDA(cudaMemcpyAsync(&okd, flag_d, 8, cudaMemcpyDeviceToHost, c->stream));
   LZ_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(dbuf);
   if (okd < 0.5) { close_peers(c); return LZ_OK; }
   c->peer_push = true;
   return lz_build_push_lists(c);
@@ -196,14 +205,21 @@ int ensure_k(lz_ctx* c, uint32_t k) {
   LZ_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(c->V);
   c->V = nv;
-  cudaFree(c->alpha); cudaFree(c->beta); cudaFree(c->hcoef); cudaFree(c->eigvals); cudaFree(c->eigvecs); cudaFree(c->eigwork); cudaFree(c->coef);
-  cudaFree(c->norm2v);
+  // k-sized arrays: allocate the new set first, swap on success, so a failed cudaMalloc leaves a consistent (old) state
+  double* fresh[8] = {};
+  const size_t bytes[8] = {(size_t)(k + 1) * 8, (size_t)k * 8, (size_t)k * 8, (size_t)k * 8, (size_t)k * 8, (size_t)k * k * 8, (size_t)k * k * 8, (size_t)k * 8};
+  for (int i = 0; i < 8; i++)
+    if (cudaMalloc((void**)&fresh[i], bytes[i]) != cudaSuccess) {
+      cudaGetLastError();
+      for (int t = 0; t < i; t++) cudaFree(fresh[t]);
+      // the basis already has k rows but the small arrays do not: fall back to "nothing allocated" rather than a half state
+      cudaFree(c->V); c->V = nullptr; c->k_cap = 0; c->have_x = false;
+      c->have_tridiag = c->have_coef = c->have_ans = false;
+      return lz_fail(LZ_ERR_ALLOC, "cannot allocate the k-sized work arrays for k = %u", k);
+    }
+  double** slot[8] = {&c->norm2v, &c->alpha, &c->beta, &c->hcoef, &c->eigvals, &c->eigvecs, &c->eigwork, &c->coef};
+  for (int i = 0; i < 8; i++) { cudaFree(*slot[i]); *slot[i] = fresh[i]; }
   c->lagged_done = false;
-  LZ_CUDA(cudaMalloc((void**)&c->norm2v, (k + 1) * 8));
-  LZ_CUDA(cudaMalloc((void**)&c->alpha, k * 8)); LZ_CUDA(cudaMalloc((void**)&c->beta, k * 8));
-  LZ_CUDA(cudaMalloc((void**)&c->hcoef, k * 8)); LZ_CUDA(cudaMalloc((void**)&c->eigvals, k * 8));
-  LZ_CUDA(cudaMalloc((void**)&c->eigvecs, (uint64_t)k * k * 8)); LZ_CUDA(cudaMalloc((void**)&c->eigwork, (uint64_t)k * k * 8));
-  LZ_CUDA(cudaMalloc((void**)&c->coef, k * 8));
   c->k_cap = k;
   c->have_tridiag = c->have_coef = c->have_ans = false;
   return LZ_OK;
@@ -308,6 +324,8 @@ static int create_body(lz_ctx* c, int device, int rank, int world, const void* u
   if (const char* e = getenv("LZ_SPMV_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) c->spmv_ctas_per_sm = (uint32_t)v; }   // tuning knob
   if (const char* e = getenv("LZ_LAGGED_NORM")) c->lagged = atoi(e) != 0;
   if (const char* e = getenv("LZ_SELL_GROUP")) { int v = atoi(e); if (v == 1 || v == 4) c->sell_group_force = (uint32_t)v; }      // test knob
+  // watchdog of the in-kernel waits on peers (seconds; 0 = none). A trap poisons the CUDA context: the ctx must be destroyed.
+  if (world > 1) LZ_TRY(lz_k_set_peer_timeout(c, getenv("LZ_PEER_TIMEOUT_S") ? atof(getenv("LZ_PEER_TIMEOUT_S")) : 20.0));
   LZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   LZ_CUDA(cudaEventCreate(&c->ev_a)); LZ_CUDA(cudaEventCreate(&c->ev_b));
   LZ_CUDA(cudaEventCreate(&c->ev_e0)); LZ_CUDA(cudaEventCreate(&c->ev_e1));
@@ -426,7 +444,9 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
   const uint64_t ldv = c->ldv;
   const bool dist = c->world > 1;
   LZ_CUDA(cudaMemsetAsync(c->status + 2, 0, sizeof(int), c->stream));
+  c->lagged_run = false;
   if (!dist && !reorth && c->lagged) {
+    c->lagged_run = true;
     // Lagged normalisation: 2 SpMV passes + ONE vector kernel per step; row j >= 1 of V keeps u_j unnormalised with
     // norm2v[j] = ||u_j||^2 (row 0 is the normalised start vector). See k_update_lagged.
     LZ_TRY(lz_k_fill(c, c->norm2v, 1, 1.0));
@@ -443,6 +463,30 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
                                   uj + ldv, c->norm2v + (j + 1), c->beta + j));
       }
     }
+    return LZ_OK;
+  }
+  if (dist && !reorth && c->lagged && c->peer_push && peer_scalars) {
+    // Lagged normalisation over the peer exchange: SpMV passes + ONE kernel per step (k_update_lagged_push): it waits for
+    // alpha, forms u_{j+1} and stores it straight into every rank's gathered vector; ||u_{j+1}||^2 is reduced off the
+    // critical path. The gathered vector holds u_j unnormalised.
+    LZ_TRY(lz_k_fill(c, c->norm2v, 1, 1.0));
+    const uint32_t push_chunks = fused_push ? 1u : c->ncolblk;
+    LZ_TRY(lz_k_scale_push(c, c->V, nullptr, c->V, nullptr, ++c->push_seq, push_chunks));   // q_0 (a previous run left its last vector there)
+    for (uint32_t j = 0; j < k; j++) {
+      double* uj = c->V + (uint64_t)j * ldv;
+      const double* q_dot = c->ncolblk == 1 ? c->xfull + (uint64_t)c->rank * c->chunk_rows : uj;
+      ++c->red_seq;
+      {
+        Scope s(c, 0);
+        LZ_TRY(lz_k_spmv_dot(c, c->xfull, q_dot, c->w, c->alpha + j, c->push_seq, fused_push ? uj : nullptr, c->red_seq));
+      }
+      if (j + 1 == k) { LZ_TRY(lz_k_lagged_finish(c, j, c->red_seq)); break; }
+      {
+        Scope s(c, 1);
+        LZ_TRY(lz_k_update_lagged_push(c, c->w, uj, j ? uj - ldv : nullptr, uj + ldv, j, ++c->push_seq, push_chunks, c->red_seq));
+      }
+    }
+    c->lagged_run = true;
     return LZ_OK;
   }
   if (dist) {   // q_0 into the gathered buffer (a previous run left q_{k-1} there)
@@ -522,6 +566,18 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
   if (const char* e = getenv("LZ_FUSED_PUSH")) fused_push = fused_push && atoi(e) != 0;
   c->ev_used = 0;
   g_marks.clear();
+  // Reduction scratch for every kernel of the loop is reserved here, once: nothing inside enqueue_steps allocates or frees
+  // (a cudaFree there would synchronise the device per step, and with one thread per GPU it can deadlock against a peer
+  // that is inside a spin kernel or an NCCL call).
+  {
+    uint64_t need = (uint64_t)c->sm_count * (c->spmv_ctas_per_sm > 8 ? c->spmv_ctas_per_sm : 8);
+    if (reorth) need = (uint64_t)c->sm_count * 4 * (k > 2 ? k : 2);
+    if (need < (uint64_t)c->sm_count * 8) need = (uint64_t)c->sm_count * 8;
+    LZ_TRY(lz_k_reserve_partials(c, need));
+  }
+  // Several GPUs: open the run with a one-element NCCL all-reduce. NCCL absorbs any start-up skew between the ranks' hosts
+  // (it simply waits), so the watchdog of the in-kernel peer waits only ever covers a peer lost in mid-run.
+  if (c->world > 1) LZ_NCCL(lz_nccl()->AllReduce(c->scal + 11, c->scal + 11, 1, ncclDouble, ncclSum, c->comm, c->stream));
   // Small problems are launch-bound (3 launches of ~10-80 us per step): replay the whole k-step loop as one CUDA graph.
   // Single GPU only (the peer exchange bakes per-run sequence numbers into kernel arguments), and not while profiling.
   bool use_graph = c->world == 1 && !c->profiling && c->n_loc <= (4u << 20);
@@ -533,8 +589,6 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
                      c->graph_V == c->V && c->graph_epoch == c->epoch;
     if (!hit) {
       drop_graph(c);
-      // no allocation may happen inside the capture: size the reduction scratch for the largest grid of the loop
-      LZ_TRY(lz_k_reserve_partials(c, (uint64_t)c->sm_count * 8 * (reorth ? (k > 8 ? k : 8) : 8)));
       const uint32_t launches0 = c->launches;
       cudaGraph_t g = nullptr;
       if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -562,7 +616,7 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
   if (!done) LZ_TRY(enqueue_steps(c, k, reorth, fused_push, peer_scalars));
   LZ_CUDA(cudaEventRecord(c->ev_b, c->stream));
   c->k_done = k;
-  c->lagged_done = c->world == 1 && !reorth && c->lagged;
+  c->lagged_done = c->lagged_run;
   c->reorth_done = reorth;
   c->have_tridiag = true;
   c->have_coef = c->have_ans = false;

@@ -142,6 +142,7 @@ struct lz_ctx {
   double* norm2v = nullptr;        // device, [k_cap + 1]: ||V[j]||^2 of the last run when the basis is stored unnormalised (lagged_done)
   bool lagged = true;              // use the lagged normalisation where it applies (one GPU, no reorthogonalisation); LZ_LAGGED_NORM=0 disables
   bool lagged_done = false;        // the last run left rows 1.. of V unnormalised
+  bool lagged_run = false;         // set by the step loop that is being enqueued
   double* scal = nullptr;          // device scalars: [0]=alpha acc, [1]=norm2 acc, [2]=x_norm, [3..] spare
   double* partials = nullptr;      // device, per-CTA partial sums
   uint32_t partials_cap = 0;
@@ -195,6 +196,11 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
 // lagged normalisation (one GPU, plain recurrence): see k_update_lagged
 int lz_k_update_lagged(lz_ctx* c, const double* t, const double* uj, const double* uprev, const double* alpha, const double* norm2_j,
                        const double* norm2_prev, double* u_next, double* norm2_out, double* beta_out);
+// lagged normalisation on several GPUs (peer exchange + peer scalars): see k_update_lagged_push
+int lz_k_update_lagged_push(lz_ctx* c, const double* t, const double* uj, const double* uprev, double* u_next, uint32_t j,
+                            unsigned long long push_seq, uint32_t push_chunks, unsigned long long red_seq);
+int lz_k_lagged_finish(lz_ctx* c, uint32_t j, unsigned long long red_seq);
+int lz_k_set_peer_timeout(lz_ctx* c, double seconds);   // watchdog of the in-kernel peer waits; <= 0 disables it
 int lz_k_coef_scale(lz_ctx* c, const double* coef, const double* norm2, uint32_t k, double* out);
 int lz_k_div_sqrt(lz_ctx* c, double* v, uint64_t n, const double* norm2);
 int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev, double* alpha, const double* beta_prev,

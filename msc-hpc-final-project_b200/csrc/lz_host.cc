@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <vector>
 
 static thread_local char g_err[512] = "";
@@ -48,32 +49,40 @@ extern "C" int lz_graph_generate_host(const lz_graph_spec* spec, uint64_t* n_out
   if (!spec || !n_out || !nnz_out || !row_offset_out || !col_idx_out) return lz_fail(LZ_ERR_ARG, "null argument");
   lz_gen_params p;
   if (lz_gen_prepare(spec, &p)) return lz_fail(LZ_ERR_ARG, "bad graph spec (kind %u)", spec->kind);
-  std::vector<uint64_t> keys;
-  keys.reserve(2 * (p.m + 1));
-  for (uint64_t e = 0; e <= p.m; e++) {
-    uint32_t u, v;
-    lz_gen_edge(p, e, &u, &v);
-    if (u == v) continue;
-    keys.push_back(((uint64_t)u << 32) | v);
-    keys.push_back(((uint64_t)v << 32) | u);
+  try {
+    std::vector<uint64_t> keys;
+    keys.reserve(2 * (p.m + 1));
+    for (uint64_t e = 0; e <= p.m; e++) {
+      uint32_t u, v;
+      lz_gen_edge(p, e, &u, &v);
+      if (u == v) continue;
+      keys.push_back(((uint64_t)u << 32) | v);
+      keys.push_back(((uint64_t)v << 32) | u);
+    }
+    *n_out = p.n;
+    return lz_build_csr_from_keys(p.n, keys.data(), keys.size(), nnz_out, row_offset_out, col_idx_out);
+  } catch (const std::exception& ex) {          // no exception crosses the C ABI
+    return lz_fail(LZ_ERR_ALLOC, "lz_graph_generate_host: %s", ex.what());
   }
-  *n_out = p.n;
-  return lz_build_csr_from_keys(p.n, keys.data(), keys.size(), nnz_out, row_offset_out, col_idx_out);
 }
 
 extern "C" int lz_csr_from_edges(uint64_t n, uint64_t n_edges, const uint32_t* u, const uint32_t* v, uint64_t* nnz_out,
                                  uint32_t** row_offset_out, uint32_t** col_idx_out) {
   if (!nnz_out || !row_offset_out || !col_idx_out || (n_edges && (!u || !v))) return lz_fail(LZ_ERR_ARG, "null argument");
   if (n == 0 || n > 0xFFFFFFFFull) return lz_fail(LZ_ERR_ARG, "bad vertex count %llu", (unsigned long long)n);
-  std::vector<uint64_t> keys;
-  keys.reserve(2 * n_edges);
-  for (uint64_t i = 0; i < n_edges; i++) {
-    if (u[i] >= n || v[i] >= n) return lz_fail(LZ_ERR_ARG, "edge %llu has a vertex out of range", (unsigned long long)i);
-    if (u[i] == v[i]) continue;
-    keys.push_back(((uint64_t)u[i] << 32) | v[i]);
-    keys.push_back(((uint64_t)v[i] << 32) | u[i]);
+  try {
+    std::vector<uint64_t> keys;
+    keys.reserve(2 * n_edges);
+    for (uint64_t i = 0; i < n_edges; i++) {
+      if (u[i] >= n || v[i] >= n) return lz_fail(LZ_ERR_ARG, "edge %llu has a vertex out of range", (unsigned long long)i);
+      if (u[i] == v[i]) continue;
+      keys.push_back(((uint64_t)u[i] << 32) | v[i]);
+      keys.push_back(((uint64_t)v[i] << 32) | u[i]);
+    }
+    return lz_build_csr_from_keys(n, keys.data(), keys.size(), nnz_out, row_offset_out, col_idx_out);
+  } catch (const std::exception& ex) {
+    return lz_fail(LZ_ERR_ALLOC, "lz_csr_from_edges: %s", ex.what());
   }
-  return lz_build_csr_from_keys(n, keys.data(), keys.size(), nnz_out, row_offset_out, col_idx_out);
 }
 
 extern "C" int lz_csr_read_text(const char* path, uint64_t* n_out, uint64_t* nnz_out, uint32_t** row_offset_out,
@@ -86,19 +95,30 @@ extern "C" int lz_csr_read_text(const char* path, uint64_t* n_out, uint64_t* nnz
     fclose(f);
     return lz_fail(LZ_ERR_IO, "%s: bad header (expected 'n n E')", path);
   }
-  std::vector<uint64_t> keys;
-  keys.reserve(2 * e);
-  for (unsigned long long i = 0; i < e; i++) {
-    unsigned long long col, row;
-    if (fscanf(f, "%llu %llu", &col, &row) != 2) { fclose(f); return lz_fail(LZ_ERR_IO, "%s: short edge list (%llu of %llu)", path, i, e); }
-    if (col < 1 || row < 1 || col > n || row > n) { fclose(f); return lz_fail(LZ_ERR_IO, "%s: vertex out of range on edge %llu", path, i); }
-    --col; --row;                                   // files are 1-based (adjMatrix.cc:31-34)
-    keys.push_back(((uint64_t)row << 32) | col);    // both triangles, duplicates collapse in the builder
-    keys.push_back(((uint64_t)col << 32) | row);
+  try {
+    std::vector<uint64_t> keys;
+    // the header is untrusted input: do not reserve what it claims beyond what the file can possibly hold (>= 4 bytes per edge)
+    long here = ftell(f);
+    fseek(f, 0, SEEK_END);
+    const unsigned long long max_edges = (unsigned long long)(ftell(f) > here ? ftell(f) - here : 0) / 4 + 1;
+    fseek(f, here, SEEK_SET);
+    keys.reserve(2 * (e < max_edges ? e : max_edges));
+    for (unsigned long long i = 0; i < e; i++) {
+      unsigned long long col, row;
+      if (fscanf(f, "%llu %llu", &col, &row) != 2) { fclose(f); return lz_fail(LZ_ERR_IO, "%s: short edge list (%llu of %llu)", path, i, e); }
+      if (col < 1 || row < 1 || col > n || row > n) { fclose(f); return lz_fail(LZ_ERR_IO, "%s: vertex out of range on edge %llu", path, i); }
+      --col; --row;                                   // files are 1-based (adjMatrix.cc:31-34)
+      keys.push_back(((uint64_t)row << 32) | col);    // both triangles, duplicates collapse in the builder
+      keys.push_back(((uint64_t)col << 32) | row);
+    }
+    fclose(f);
+    f = nullptr;
+    *n_out = n;
+    return lz_build_csr_from_keys(n, keys.data(), keys.size(), nnz_out, row_offset_out, col_idx_out);
+  } catch (const std::exception& ex) {
+    if (f) fclose(f);
+    return lz_fail(LZ_ERR_ALLOC, "lz_csr_read_text: %s", ex.what());
   }
-  fclose(f);
-  *n_out = n;
-  return lz_build_csr_from_keys(n, keys.data(), keys.size(), nnz_out, row_offset_out, col_idx_out);
 }
 
 extern "C" int lz_csr_write_text(const char* path, uint64_t n, const uint32_t* row_offset, const uint32_t* col_idx) {

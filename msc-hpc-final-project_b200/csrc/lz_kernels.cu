@@ -54,6 +54,11 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 // and adds them in rank order, so all ranks obtain the bit-identical sum without a collective launch in between.
 // Two parities suffice: a rank can be at most one reduction of a kind ahead of its slowest peer (the vector exchange
 // of the step in between needs every rank's contribution).
+// Watchdog of the in-kernel spins (wait_chunk, red_consume): nanoseconds after which a peer that never arrives turns into a
+// launch failure (__trap: the CUDA context is then unusable and must be destroyed) instead of a silent hang. 0 = wait for ever,
+// which is what NCCL would do. Set per device from LZ_PEER_TIMEOUT_S (default 20 s) by lz_k_set_peer_timeout.
+__device__ unsigned long long g_peer_timeout_ns = 20000000000ull;
+
 struct lz_red_slot { double val; unsigned long long seq; };
 struct lz_red {
   lz_red_slot* area[LZ_MAX_WORLD];   // exchange area of every rank as seen from this GPU: [2 kinds][2][LZ_MAX_WORLD]
@@ -67,23 +72,25 @@ __device__ __forceinline__ void red_publish(const lz_red& red, int kind, double 
   for (uint32_t r = 0; r < red.world; r++)                                // ... then the sequence numbers
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&red.area[r][idx].seq), "l"(red.seq) : "memory");
 }
-// All threads of the CTA call this; returns the total in every thread.
-__device__ __forceinline__ double red_consume(const lz_red& red, int kind, double* sm_bcast) {
+// All threads of the CTA call this; returns the total of reduction `seq` of `kind` in every thread.
+__device__ __forceinline__ double red_consume_seq(const lz_red& red, int kind, unsigned long long seq, double* sm_bcast) {
+  __syncthreads();   // sm_bcast may still be read from a previous call
   if (threadIdx.x == 0) {
-    const lz_red_slot* base = red.area[red.rank] + ((size_t)kind * 2 + (red.seq & 1)) * LZ_MAX_WORLD;
+    const lz_red_slot* base = red.area[red.rank] + ((size_t)kind * 2 + (seq & 1)) * LZ_MAX_WORLD;
+    const unsigned long long limit = g_peer_timeout_ns;
     double tot = 0.0;
     for (uint32_t r = 0; r < red.world; r++) {
       unsigned long long got, t0 = 0;
       unsigned int spins = 0;
       for (;;) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&base[r].seq) : "memory");
-        if (got >= red.seq) break;
+        if (got >= seq) break;
         __nanosleep(32);
-        if ((++spins & 0xFFFFu) == 0) {
+        if (limit && (++spins & 0xFFFFu) == 0) {
           unsigned long long now;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
           if (t0 == 0) t0 = now;
-          else if (now - t0 > 20000000000ull) __trap();
+          else if (now - t0 > limit) __trap();
         }
       }
       tot += *reinterpret_cast<const volatile double*>(&base[r].val);
@@ -92,6 +99,9 @@ __device__ __forceinline__ double red_consume(const lz_red& red, int kind, doubl
   }
   __syncthreads();
   return *sm_bcast;
+}
+__device__ __forceinline__ double red_consume(const lz_red& red, int kind, double* sm_bcast) {
+  return red_consume_seq(red, kind, red.seq, sm_bcast);
 }
 
 // Deterministic grid reduction tail. Thread 0 of every CTA passes its CTA value; the last CTA to arrive sums all
@@ -150,15 +160,16 @@ __device__ __forceinline__ void wait_chunk(const unsigned long long* flags, uint
   if (seq == 0) return;
   if (threadIdx.x < world) {
     const unsigned long long* f = flags + (uint64_t)blk * LZ_MAX_WORLD + threadIdx.x;
+    const unsigned long long limit = g_peer_timeout_ns;
     unsigned long long t0 = 0;
     unsigned int spins = 0;
     while (ld_acquire_sys(f) < seq) {
       __nanosleep(64);
-      if ((++spins & 0xFFFFu) == 0) {                      // watchdog: a lost peer becomes a launch failure, not a hang
+      if (limit && (++spins & 0xFFFFu) == 0) {             // watchdog: a lost peer becomes a launch failure, not a hang
         unsigned long long now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         if (t0 == 0) t0 = now;
-        else if (now - t0 > 20000000000ull) __trap();      // 20 s
+        else if (now - t0 > limit) __trap();
       }
     }
   }
@@ -204,10 +215,24 @@ __device__ __forceinline__ void push_chunk(const double* __restrict__ src, const
 // 2R gathers, then the sums — and CTAs are persistent (static item-stride loop), so the reduction tail is paid once.
 constexpr int kSpmvR = LZ_SPMV_ROWS_PER_GROUP;
 
-template <int LG, int PER>
+// The gathered vector. One GPU: read-only for the whole kernel -> ld.global.nc. Several GPUs: the peers write it while this
+// kernel is resident (it starts, acquires the chunk's arrival counters, then reads), so the non-coherent path is not allowed
+// there: plain ld.global, which the acquire + bar.sync of wait_chunk orders after the peers' released stores.
+template <bool PEER>
+__device__ __forceinline__ double ldx(const double* x, uint32_t c) {
+  if constexpr (PEER) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(x + c));
+    return v;
+  } else {
+    return __ldg(x + c);
+  }
+}
+
+template <int LG, int PER, bool PEER>
 __device__ __forceinline__ double spmv_item(const lz_spmv_bin& bin, uint32_t item, const uint32_t* __restrict__ seg_lo,
                                             const uint32_t* __restrict__ seg_hi, const uint32_t* __restrict__ col,
-                                            const double* __restrict__ x, const double* __restrict__ q, double* __restrict__ w,
+                                            const double* x, const double* q, double* __restrict__ w,
                                             bool accumulate, bool final_pass) {
   constexpr uint32_t L = 1u << LG;
   constexpr uint32_t GROUPS = kBlock >> LG;
@@ -239,7 +264,7 @@ __device__ __forceinline__ double spmv_item(const lz_spmv_bin& bin, uint32_t ite
 #pragma unroll
     for (int r = 0; r < kSpmvR; r++)
 #pragma unroll
-      for (int u = 0; u < PER; u++) v[r][u] = p[r][u] ? __ldg(x + c[r][u]) : 0.0;
+      for (int u = 0; u < PER; u++) v[r][u] = p[r][u] ? ldx<PEER>(x, c[r][u]) : 0.0;
 #pragma unroll
     for (int r = 0; r < kSpmvR; r++) {
       double s = v[r][0];
@@ -260,7 +285,7 @@ __device__ __forceinline__ double spmv_item(const lz_spmv_bin& bin, uint32_t ite
       for (int u = 0; u < PER; u++) cc[u] = (j0 + u * L < e[r]) ? __ldcs(col + j0 + u * L) : 0xFFFFFFFFu;
       double vv[PER];
 #pragma unroll
-      for (int u = 0; u < PER; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? __ldg(x + cc[u]) : 0.0;
+      for (int u = 0; u < PER; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? ldx<PEER>(x, cc[u]) : 0.0;
       double s = 0.0;
 #pragma unroll
       for (int u = 0; u < PER; u++) s += vv[u];
@@ -290,9 +315,10 @@ __device__ __forceinline__ double spmv_item(const lz_spmv_bin& bin, uint32_t ite
 }
 
 // One pass = one column block. accumulate: w += (pass > 0). final_pass: also alpha partial = w . q and the grid reduction.
+template <bool PEER>
 __global__ void __launch_bounds__(kBlock) k_spmv_dot(const __grid_constant__ lz_spmv_plan plan, const uint32_t* __restrict__ seg_lo,
                                                      const uint32_t* __restrict__ seg_hi, const uint32_t* __restrict__ col,
-                                                     const double* __restrict__ x, const double* __restrict__ q, double* __restrict__ w,
+                                                     const double* x, const double* q, double* __restrict__ w,
                                                      double* partials, unsigned int* ticket, double* alpha_out, int accumulate,
                                                      int final_pass, const unsigned long long* flags, uint32_t blk, uint32_t world,
                                                      unsigned long long wait_seq, const double* alpha_div) {
@@ -308,7 +334,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_dot(const __grid_constant__ lz_
       if (i < plan.nbins && item >= plan.bin[i].item_begin) bi = i;
     const lz_spmv_bin& bin = plan.bin[bi];
     const uint32_t it = item - bin.item_begin;
-#define LZ_SPMV_CASE(LG, PER) d += spmv_item<LG, PER>(bin, it, seg_lo, seg_hi, col, x, q, w, acc, fin)
+#define LZ_SPMV_CASE(LG, PER) d += spmv_item<LG, PER, PEER>(bin, it, seg_lo, seg_hi, col, x, q, w, acc, fin)
     switch (bin.log2_lanes) {
       case 5:
         if (bin.per_lane == 2) LZ_SPMV_CASE(5, 2);
@@ -338,10 +364,10 @@ __global__ void __launch_bounds__(kBlock) k_spmv_dot(const __grid_constant__ lz_
 // in flight instead of one slice's 3-6 — such a block is latency-bound otherwise. Costs registers (3 CTAs/SM instead of
 // 6), so it is a separate instantiation chosen per column block at ingest. Summation order per row is unchanged.
 constexpr int kSellU = 8;   // chunks (gathers per lane) in flight
-template <bool NARROW>
+template <bool NARROW, bool PEER>
 __global__ void __launch_bounds__(kBlock, NARROW ? 4 : 6) k_spmv_sell(const uint32_t* __restrict__ sp, const uint32_t* __restrict__ scol, uint32_t n_long,
-                                                      uint32_t n_items, uint32_t n_loc, const double* __restrict__ x,
-                                                      const double* __restrict__ q, double* __restrict__ w, double* partials,
+                                                      uint32_t n_items, uint32_t n_loc, const double* x,
+                                                      const double* q, double* __restrict__ w, double* partials,
                                                       unsigned int* ticket, double* alpha_out, int accumulate, int final_pass,
                                                       const unsigned long long* flags, uint32_t blk, uint32_t world,
                                                       unsigned long long wait_seq, const __grid_constant__ lz_push_job job,
@@ -390,7 +416,7 @@ __global__ void __launch_bounds__(kBlock, NARROW ? 4 : 6) k_spmv_sell(const uint
 #pragma unroll
         for (int t = 0; t < 4; t++)
 #pragma unroll
-          for (int u = 0; u < 4; u++) vv[t][u] = (cc[t][u] != 0xFFFFFFFFu) ? __ldg(x + cc[t][u]) : 0.0;
+          for (int u = 0; u < 4; u++) vv[t][u] = (cc[t][u] != 0xFFFFFFFFu) ? ldx<PEER>(x, cc[t][u]) : 0.0;
 #pragma unroll
         for (int t = 0; t < 4; t++)
 #pragma unroll
@@ -426,7 +452,7 @@ __global__ void __launch_bounds__(kBlock, NARROW ? 4 : 6) k_spmv_sell(const uint
 #pragma unroll
       for (int t = 0; t < 4; t++)
 #pragma unroll
-        for (int u = 0; u < 2; u++) vv[t][u] = (cc[t][u] != 0xFFFFFFFFu) ? __ldg(x + cc[t][u]) : 0.0;
+        for (int u = 0; u < 2; u++) vv[t][u] = (cc[t][u] != 0xFFFFFFFFu) ? ldx<PEER>(x, cc[t][u]) : 0.0;
 #pragma unroll
       for (int t = 0; t < 4; t++) {
         const uint32_t item = first + t;
@@ -457,7 +483,7 @@ __global__ void __launch_bounds__(kBlock, NARROW ? 4 : 6) k_spmv_sell(const uint
         for (int u = 0; u < kSellU; u++) cc[u] = __ldcs(p + (uint64_t)(j + u) * 32);
         double vv[kSellU];
 #pragma unroll
-        for (int u = 0; u < kSellU; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? __ldg(x + cc[u]) : 0.0;
+        for (int u = 0; u < kSellU; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? ldx<PEER>(x, cc[u]) : 0.0;
 #pragma unroll
         for (int u = 0; u < kSellU; u++) acc += vv[u];
       }
@@ -468,7 +494,7 @@ __global__ void __launch_bounds__(kBlock, NARROW ? 4 : 6) k_spmv_sell(const uint
         for (int u = 0; u < kSellU - 1; u++) cc[u] = (u < (int)rem) ? __ldcs(p + (uint64_t)(j + u) * 32) : 0xFFFFFFFFu;
         double vv[kSellU];
 #pragma unroll
-        for (int u = 0; u < kSellU - 1; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? __ldg(x + cc[u]) : 0.0;
+        for (int u = 0; u < kSellU - 1; u++) vv[u] = (cc[u] != 0xFFFFFFFFu) ? ldx<PEER>(x, cc[u]) : 0.0;
 #pragma unroll
         for (int u = 0; u < kSellU - 1; u++) acc += vv[u];
       }
@@ -553,6 +579,13 @@ __global__ void __launch_bounds__(kBlock) k_update_norm(double* __restrict__ w, 
 //   u_{j+1} = t/||u_j|| - alpha_j q_j - beta_{j-1} q_{j-1},   beta_{j-1} = ||u_j||,   beta_j = ||u_{j+1}||
 // which is the reference's recurrence (lanczos.cu:32-50) with the division by beta moved to the consumers (as a multiplication
 // by the reciprocal: results differ from the divide-first order in the last bit only).
+// One entry of the lagged update, u' = (t - alpha u_j) / ||u_j|| - (||u_j|| / ||u_{j-1}||) u_{j-1}, with the operation order pinned by
+// explicit fma so that every kernel that forms it (one GPU, dense push, entry-wise push) produces the same bits.
+__device__ __forceinline__ double lagged_entry(double t, double q, double p, double a, double rj, double cp, bool has_p) {
+  double v = fma(-a, q, t) * rj;
+  if (has_p) v = fma(-cp, p, v);
+  return v;
+}
 __global__ void __launch_bounds__(kBlock) k_update_lagged(const double* __restrict__ t, const double* __restrict__ uj, const double* __restrict__ up,
                                                           const double* __restrict__ alpha_p, const double* __restrict__ norm2_j,
                                                           const double* __restrict__ norm2_p, uint64_t n, double* __restrict__ u_next,
@@ -573,23 +606,18 @@ __global__ void __launch_bounds__(kBlock) k_update_lagged(const double* __restri
   double2* o2 = reinterpret_cast<double2*>(u_next);
   for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
     const double2 tv = t2[i], qv = q2[i];
+    const double2 pv = up ? p2[i] : make_double2(0.0, 0.0);
     double2 v;
-    v.x = (tv.x - a * qv.x) * rj;
-    v.y = (tv.y - a * qv.y) * rj;
-    if (up) {
-      const double2 pv = p2[i];
-      v.x -= cp * pv.x;
-      v.y -= cp * pv.y;
-    }
+    v.x = lagged_entry(tv.x, qv.x, pv.x, a, rj, cp, up != nullptr);
+    v.y = lagged_entry(tv.y, qv.y, pv.y, a, rj, cp, up != nullptr);
     o2[i] = v;
-    acc += v.x * v.x;
-    acc += v.y * v.y;
+    acc = fma(v.x, v.x, acc);
+    acc = fma(v.y, v.y, acc);
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    double v = (t[n - 1] - a * uj[n - 1]) * rj;
-    if (up) v -= cp * up[n - 1];
+    const double v = lagged_entry(t[n - 1], uj[n - 1], up ? up[n - 1] : 0.0, a, rj, cp, up != nullptr);
     u_next[n - 1] = v;
-    acc += v * v;
+    acc = fma(v, v, acc);
   }
   acc = block_sum(acc, sm);
   if (threadIdx.x == 0) {
@@ -610,6 +638,121 @@ __global__ void __launch_bounds__(kBlock) k_update_lagged(const double* __restri
     }
   }
 }
+// Lagged normalisation on several GPUs (plain recurrence, peer exchange): the same update as k_update_lagged, fused with the
+// two cross-GPU reductions it depends on and with the producer side of the vector exchange, so one step is the SpMV passes plus
+// THIS kernel — the separate normalisation kernel (k_scale_push) and its cross-GPU wait are gone:
+//   * alpha_j = (sum over ranks of the SpMV kernels' partials of A u_j . u_j) / ||u_j||^2  — consumed from the peer scalar slots;
+//   * ||u_j||^2 was published by the previous step's instance of this kernel (long arrived: not on the critical path);
+//   * u_{j+1} is written to the local basis AND — unnormalised — straight into every rank's gathered vector (chunks
+//     [0, push_chunks); the SpMV passes send the rest), or entry-wise to the peers that reference it (needed-columns exchange);
+//   * the partial of ||u_{j+1}||^2 is published for the next step. Nobody waits for it inside this step.
+// The peers' SpMV gathers from the unnormalised vector; every consumer of V folds 1/||u_j|| in (multOut, lz_get_basis).
+struct lz_push_lists {
+  const uint32_t* list;
+  uint32_t off[LZ_MAX_WORLD + 1];
+};
+template <bool SPARSE>
+__global__ void __launch_bounds__(kBlock) k_update_lagged_push(const double* __restrict__ t, const double* __restrict__ uj, const double* __restrict__ up,
+                                                               uint64_t n, double* __restrict__ u_next, double* __restrict__ norm2v /* [j] is written here */,
+                                                               uint32_t j, double* __restrict__ alpha_out, double* __restrict__ beta_out,
+                                                               const __grid_constant__ lz_peers peers, uint64_t cl, uint32_t nchunks, uint32_t push_chunks,
+                                                               uint32_t world, uint32_t rank, unsigned long long push_seq, unsigned int* push_ticket,
+                                                               double* partials, unsigned int* ticket, const __grid_constant__ lz_red red,
+                                                               const __grid_constant__ lz_push_lists lists) {
+  __shared__ double sm[kWarps];
+  __shared__ bool s_last;
+  __shared__ double s_bcast;
+  // ||u_j||^2 first (published one step ago), then alpha (the reduction this step waits for)
+  const double n2j = j ? red_consume_seq(red, 1, red.seq - 1, &s_bcast) : 1.0;
+  const double a = red_consume_seq(red, 0, red.seq, &s_bcast) / n2j;
+  const double nj = sqrt(n2j);
+  const double rj = 1.0 / nj;
+  const double cp = up ? nj / sqrt(norm2v[j - 1]) : 0.0;      // norm2v[j-1]: written by the previous launch of this kernel
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    alpha_out[j] = a;
+    if (j) { norm2v[j] = n2j; beta_out[j - 1] = nj; }
+  }
+  const double2* t2 = reinterpret_cast<const double2*>(t);
+  const double2* q2 = reinterpret_cast<const double2*>(uj);
+  const double2* p2 = reinterpret_cast<const double2*>(up);
+  double2* o2 = reinterpret_cast<double2*>(u_next);
+  const uint64_t cl2 = cl >> 1;
+  double acc = 0.0;
+  double* own = peers.x[rank];
+  for (uint32_t c = 0; c < nchunks; c++) {
+    const bool send = !SPARSE && c < push_chunks;
+    const uint64_t slot2 = ((uint64_t)c * world * cl + (uint64_t)rank * cl) >> 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < cl2; i += (uint64_t)gridDim.x * kBlock) {
+      const uint64_t li = (uint64_t)c * cl2 + i;
+      const double2 tv = t2[li], qv = q2[li];
+      const double2 pv = up ? p2[li] : make_double2(0.0, 0.0);
+      double2 v;
+      v.x = lagged_entry(tv.x, qv.x, pv.x, a, rj, cp, up != nullptr);
+      v.y = lagged_entry(tv.y, qv.y, pv.y, a, rj, cp, up != nullptr);
+      o2[li] = v;
+      acc = fma(v.x, v.x, acc);
+      acc = fma(v.y, v.y, acc);
+      if (SPARSE) reinterpret_cast<double2*>(own)[slot2 + i] = v;
+      else if (send)
+        for (uint32_t r = 0; r < world; r++) reinterpret_cast<double2*>(peers.x[r])[slot2 + i] = v;
+    }
+    if (!send) continue;
+    __threadfence_system();          // this thread's peer stores are visible system-wide before the CTA reports in
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int tk = atomicAdd(push_ticket + c, 1u);
+      s_last = (tk == gridDim.x - 1);
+      if (s_last) {
+        push_ticket[c] = 0u;
+        __threadfence_system();
+        for (uint32_t r = 0; r < world; r++) st_release_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, push_seq);
+      }
+    }
+    __syncthreads();
+  }
+  if (SPARSE) {
+    // every peer receives only the entries its rows reference; the values are recomputed from the inputs (same operations =>
+    // same bits as the local copy), because the entry may have been produced by another CTA of this launch
+    for (uint32_t r = 0; r < world; r++) {
+      if (r == rank) continue;
+      double* dst = peers.x[r];
+      const uint32_t e = lists.off[r + 1];
+      for (uint64_t s = (uint64_t)lists.off[r] + (uint64_t)blockIdx.x * kBlock + threadIdx.x; s < e; s += (uint64_t)gridDim.x * kBlock) {
+        const uint32_t l = __ldg(lists.list + s);
+        const double v = lagged_entry(t[l], uj[l], up ? up[l] : 0.0, a, rj, cp, up != nullptr);
+        const uint64_t c = l / cl;
+        dst[c * (world * cl) + (uint64_t)rank * cl + (l - c * cl)] = v;
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int tk = atomicAdd(push_ticket, 1u);
+      s_last = (tk == gridDim.x - 1);
+      if (s_last) {
+        *push_ticket = 0u;
+        __threadfence_system();
+        for (uint32_t c = 0; c < nchunks; c++)
+          for (uint32_t r = 0; r < world; r++) st_release_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, push_seq);
+      }
+    }
+    __syncthreads();
+  }
+  acc = block_sum(acc, sm);
+  grid_sum_finish(acc, partials, ticket, nullptr, sm, &s_last, 0xFFFFFFFFu, 0, &red, 1);   // publishes the partial of ||u_{j+1}||^2
+}
+// Closes a lagged multi-GPU run: the last step has no update kernel, so its alpha and the last ||u||^2 are finished here.
+__global__ void k_lagged_finish(uint32_t j, double* __restrict__ norm2v, double* __restrict__ alpha_out, double* __restrict__ beta_out,
+                                const __grid_constant__ lz_red red) {
+  __shared__ double s_bcast;
+  const double n2j = j ? red_consume_seq(red, 1, red.seq - 1, &s_bcast) : 1.0;
+  const double a = red_consume_seq(red, 0, red.seq, &s_bcast) / n2j;
+  if (threadIdx.x == 0) {
+    alpha_out[j] = a;
+    if (j) { norm2v[j] = n2j; beta_out[j - 1] = sqrt(n2j); }
+  }
+}
+
 // out[j] = coef[j] / sqrt(norm2[j]): multOut coefficients for an unnormalised basis
 __global__ void k_coef_scale(const double* __restrict__ coef, const double* __restrict__ norm2, uint32_t k, double* __restrict__ out) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -693,10 +836,6 @@ __global__ void __launch_bounds__(kBlock) k_scale_push(const double* __restrict_
 // rank's own slots of the gathered vector in full; every peer receives only the entries its rows reference (8-byte peer
 // stores over NVLink, ascending addresses). One arrival counter per chunk is raised at the end, as in k_scale_push, so the
 // consuming SpMV passes are unchanged. Remote values are recomputed from w (same division => same bits as the local copy).
-struct lz_push_lists {
-  const uint32_t* list;
-  uint32_t off[LZ_MAX_WORLD + 1];
-};
 __global__ void __launch_bounds__(kBlock) k_scale_push_sparse(const double* __restrict__ w, const double* __restrict__ norm2_p, uint64_t n,
                                                               double* __restrict__ q_next, const __grid_constant__ lz_peers peers, uint64_t cl,
                                                               uint32_t nchunks, uint32_t world, uint32_t rank, unsigned long long seq,
@@ -1131,7 +1270,8 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
       if (grid < 1) grid = 1;
       LZ_TRY(ensure_partials(c, grid));
       grid += job.nctas;
-      auto kern = narrow ? k_spmv_sell<true> : k_spmv_sell<false>;
+      const bool peer = c->world > 1;
+      auto kern = narrow ? (peer ? k_spmv_sell<true, true> : k_spmv_sell<true, false>) : (peer ? k_spmv_sell<false, true> : k_spmv_sell<false, false>);
       kern<<<grid, kBlock, 0, c->stream>>>(c->sell_sp + (uint64_t)blk * c->n_items, c->sell_col, c->n_long, c->n_items,
                                            (uint32_t)c->n_loc, x_gather, q_local, w_out, c->partials, c->ticket + 0, alpha_out, acc, fin,
                                            c->flags, blk, (uint32_t)c->world, wait_seq, job, group, red, alpha_div);
@@ -1141,8 +1281,9 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
       uint32_t grid = (uint32_t)c->sm_count * c->spmv_ctas_per_sm;
       if (grid > plan.nitems) grid = plan.nitems;
       LZ_TRY(ensure_partials(c, grid));
-      k_spmv_dot<<<grid, kBlock, 0, c->stream>>>(plan, c->seg[blk], c->seg[blk] + 1, c->col, x_gather, q_local, w_out, c->partials,
-                                                 c->ticket + 0, alpha_out, acc, fin, c->flags, blk, (uint32_t)c->world, wait_seq, alpha_div);
+      auto kern = c->world > 1 ? k_spmv_dot<true> : k_spmv_dot<false>;
+      kern<<<grid, kBlock, 0, c->stream>>>(plan, c->seg[blk], c->seg[blk] + 1, c->col, x_gather, q_local, w_out, c->partials,
+                                           c->ticket + 0, alpha_out, acc, fin, c->flags, blk, (uint32_t)c->world, wait_seq, alpha_div);
     }
     LZ_LAUNCH_CHECK();
   }
@@ -1167,6 +1308,34 @@ int lz_k_update_lagged(lz_ctx* c, const double* t, const double* uj, const doubl
   k_update_lagged<<<g, kBlock, 0, c->stream>>>(t, uj, uprev, alpha, norm2_j, norm2_prev, c->n_loc, u_next, c->partials, c->ticket + 1,
                                                norm2_out, beta_out);
   LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+int lz_k_update_lagged_push(lz_ctx* c, const double* t, const double* uj, const double* uprev, double* u_next, uint32_t j,
+                            unsigned long long push_seq, uint32_t push_chunks, unsigned long long red_seq) {
+  lz_peers peers;
+  for (int r = 0; r < LZ_MAX_WORLD; r++) { peers.x[r] = c->peer_xfull[r]; peers.f[r] = c->peer_flags[r]; }
+  lz_push_lists lists;
+  lists.list = c->push_list;
+  for (int r = 0; r <= LZ_MAX_WORLD; r++) lists.off[r] = c->push_off[r];
+  // the same grid whatever the exchange mode: the partition of the ||u||^2 partial sums (hence its bits) must not depend on it
+  unsigned g = stream_grid(c, c->chunk_rows / 2 + 1);
+  const unsigned cap = (unsigned)c->sm_count * 4;
+  if (g > cap) g = cap;
+  LZ_TRY(ensure_partials(c, g));
+  auto kern = c->sparse_push ? k_update_lagged_push<true> : k_update_lagged_push<false>;
+  kern<<<g, kBlock, 0, c->stream>>>(t, uj, uprev, c->n_loc, u_next, c->norm2v, j, c->alpha, c->beta, peers, c->chunk_rows, c->ncolblk, push_chunks,
+                                    (uint32_t)c->world, (uint32_t)c->rank, push_seq, c->push_ticket, c->partials, c->ticket + 1, make_red(c, red_seq), lists);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+int lz_k_lagged_finish(lz_ctx* c, uint32_t j, unsigned long long red_seq) {
+  k_lagged_finish<<<1, 32, 0, c->stream>>>(j, c->norm2v, c->alpha, c->beta, make_red(c, red_seq));
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+int lz_k_set_peer_timeout(lz_ctx* c, double seconds) {
+  const unsigned long long ns = seconds <= 0.0 ? 0ull : (unsigned long long)(seconds * 1e9);
+  LZ_CUDA(cudaMemcpyToSymbol(g_peer_timeout_ns, &ns, sizeof(ns)));
   return LZ_OK;
 }
 int lz_k_coef_scale(lz_ctx* c, const double* coef, const double* norm2, uint32_t k, double* out) {
