@@ -193,6 +193,10 @@ int lz_timings_get(lz_ctx* ctx, lz_timings* out);
 /* cudaEvent stopwatch on the ctx stream, for callers that time several calls as one region (bench.py). */
 int lz_timer_start(lz_ctx* ctx);
 int lz_timer_stop(lz_ctx* ctx, float* ms_out); /* synchronises on the stop event */
+/* Device-side timeline of the kernels' internal phases (start, wait for the peers over, push done, end): tells waiting for peers
+ * apart from work inside the fused kernels, which stream events cannot. cap_events > 0: switch on and clear. cap_events == 0: read
+ * back into out ((tag, globaltimer ns) pairs; tag = kernel << 8 | phase, see lz_kernels.cu) and switch off. Measurement only. */
+int lz_debug_trace(lz_ctx* ctx, uint32_t cap_events, uint64_t* out, uint32_t out_cap_events, uint32_t* count_out);
 /* Writes >= bytes of device memory (L2 flush between timed repetitions). */
 int lz_flush_l2(lz_ctx* ctx);
 

@@ -110,6 +110,7 @@ _sig("lz_timings_get", _ctx, _P(Timings))
 _sig("lz_timer_start", _ctx)
 _sig("lz_timer_stop", _ctx, _P(C.c_float))
 _sig("lz_flush_l2", _ctx)
+_sig("lz_debug_trace", _ctx, C.c_uint32, _u64p, C.c_uint32, _u32p)
 
 
 def _check(rc):
@@ -361,6 +362,15 @@ class Context:
         ms = C.c_float(0)
         _check(lib.lz_timer_stop(self._h, C.byref(ms)))
         return ms.value
+
+    def trace_on(self, cap=4096):
+        _check(lib.lz_debug_trace(self._h, cap, None, 0, None))
+
+    def trace_read(self, cap=4096):
+        """-> array [(tag, ns)] in order of arrival; switches the timeline off."""
+        buf, cnt = np.empty((cap, 2), np.uint64), C.c_uint32(0)
+        _check(lib.lz_debug_trace(self._h, 0, buf.ctypes.data_as(_u64p), cap, C.byref(cnt)))
+        return buf[:cnt.value]
 
     def flush_l2(self):
         _check(lib.lz_flush_l2(self._h))

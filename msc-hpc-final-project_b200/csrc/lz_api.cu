@@ -323,6 +323,7 @@ static int create_body(lz_ctx* c, int device, int rank, int world, const void* u
   if (const char* e = getenv("LZ_SPMV_VARIANT")) { int v = atoi(e); if (v >= 0 && v <= LZ_SPMV_WARP) c->spmv_variant = v; }     // tuning knob
   if (const char* e = getenv("LZ_SPMV_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) c->spmv_ctas_per_sm = (uint32_t)v; }   // tuning knob
   if (const char* e = getenv("LZ_LAGGED_NORM")) c->lagged = atoi(e) != 0;
+  if (const char* e = getenv("LZ_PUSH_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 1024) c->push_ctas = (uint32_t)v; }        // tuning knob
   if (const char* e = getenv("LZ_SELL_GROUP")) { int v = atoi(e); if (v == 1 || v == 4) c->sell_group_force = (uint32_t)v; }      // test knob
   // watchdog of the in-kernel waits on peers (seconds; 0 = none). A trap poisons the CUDA context: the ctx must be destroyed.
   if (world > 1) LZ_TRY(lz_k_set_peer_timeout(c, getenv("LZ_PEER_TIMEOUT_S") ? atof(getenv("LZ_PEER_TIMEOUT_S")) : 20.0));
@@ -385,6 +386,7 @@ extern "C" int lz_destroy(lz_ctx* c) {
   free_vectors(c);
   lz_free_graph(c);
   lz_free_rank(c);
+  cudaFree(c->trace_buf);
   cudaFree(c->scal); cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->status); cudaFree(c->flush_buf);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : {c->ev_a, c->ev_b, c->ev_e0, c->ev_e1, c->ev_m0, c->ev_m1, c->ev_t0, c->ev_t1})
@@ -843,6 +845,36 @@ extern "C" int lz_get_basis(lz_ctx* c, uint32_t j, double* q_host) {
 extern "C" int lz_set_profiling(lz_ctx* c, int on) {
   if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
   c->profiling = on != 0;
+  return LZ_OK;
+}
+
+// Measurement hook: device-side timeline of the kernels' internal phases (start, peer wait over, push done, end).
+// cap_events > 0 switches the timeline on (and clears it); cap_events == 0 reads it back: out receives (tag, ns) pairs.
+extern "C" int lz_debug_trace(lz_ctx* c, uint32_t cap_events, uint64_t* out, uint32_t out_cap_events, uint32_t* count_out) {
+  if (!c) return lz_fail(LZ_ERR_ARG, "null ctx");
+  LZ_TRY(set_dev(c));
+  if (cap_events) {
+    if (c->trace_cap < cap_events) {
+      LZ_CUDA(cudaStreamSynchronize(c->stream));
+      cudaFree(c->trace_buf); c->trace_buf = nullptr; c->trace_cap = 0;
+      LZ_CUDA(cudaMalloc((void**)&c->trace_buf, (2 + 2 * (size_t)cap_events) * 8));
+      c->trace_cap = cap_events;
+    }
+    const unsigned long long head[2] = {0ull, cap_events};
+    LZ_CUDA(cudaMemcpyAsync(c->trace_buf, head, sizeof(head), cudaMemcpyHostToDevice, c->stream));
+    LZ_TRY(lz_k_set_trace(c, c->trace_buf));
+    LZ_CUDA(cudaStreamSynchronize(c->stream));
+    return LZ_OK;
+  }
+  if (!c->trace_buf) return lz_fail(LZ_ERR_ARG, "trace is not on");
+  LZ_TRY(lz_k_set_trace(c, nullptr));
+  unsigned long long head[2] = {0, 0};
+  LZ_CUDA(cudaMemcpyAsync(head, c->trace_buf, sizeof(head), cudaMemcpyDeviceToHost, c->stream));
+  LZ_CUDA(cudaStreamSynchronize(c->stream));
+  uint32_t cnt = (uint32_t)(head[0] < head[1] ? head[0] : head[1]);
+  if (cnt > out_cap_events) cnt = out_cap_events;
+  if (out && cnt) LZ_CUDA(cudaMemcpy(out, c->trace_buf + 2, (size_t)cnt * 16, cudaMemcpyDeviceToHost));
+  if (count_out) *count_out = cnt;
   return LZ_OK;
 }
 

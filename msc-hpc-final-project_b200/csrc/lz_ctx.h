@@ -125,6 +125,7 @@ struct lz_ctx {
   lz_spmv_plan plan_auto[LZ_MAX_COLBLK] = {}, plan_warp{};
   int spmv_variant = LZ_SPMV_AUTO;
   uint32_t spmv_ctas_per_sm = 6;   // persistent SpMV grid = sm_count * this
+  uint32_t push_ctas = 0;          // sender CTAs fused into an SpMV pass (0 = sm_count / 4; LZ_PUSH_CTAS)
   uint32_t sell_group_force = 0;   // 0 = automatic; 1 or 4 = items per work unit of the sliced kernel (LZ_SELL_GROUP, tests)
 
   // ---- vectors ----------------------------------------------------------------------------------------------------
@@ -177,6 +178,8 @@ struct lz_ctx {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   lz_timings tm{};
+  unsigned long long* trace_buf = nullptr;   // device, lz_debug_trace
+  uint32_t trace_cap = 0;
   uint32_t launches = 0;
 };
 
@@ -200,6 +203,7 @@ int lz_k_update_lagged(lz_ctx* c, const double* t, const double* uj, const doubl
 int lz_k_update_lagged_push(lz_ctx* c, const double* t, const double* uj, const double* uprev, double* u_next, uint32_t j,
                             unsigned long long push_seq, uint32_t push_chunks, unsigned long long red_seq);
 int lz_k_lagged_finish(lz_ctx* c, uint32_t j, unsigned long long red_seq);
+int lz_k_set_trace(lz_ctx* c, unsigned long long* buf_device);   // device timeline on (buffer) / off (null)
 int lz_k_set_peer_timeout(lz_ctx* c, double seconds);   // watchdog of the in-kernel peer waits; <= 0 disables it
 int lz_k_coef_scale(lz_ctx* c, const double* coef, const double* norm2, uint32_t k, double* out);
 int lz_k_div_sqrt(lz_ctx* c, double* v, uint64_t n, const double* norm2);

@@ -59,6 +59,24 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 // which is what NCCL would do. Set per device from LZ_PEER_TIMEOUT_S (default 20 s) by lz_k_set_peer_timeout.
 __device__ unsigned long long g_peer_timeout_ns = 20000000000ull;
 
+// Optional device-side timeline (lz_debug_trace): (tag, globaltimer) pairs appended by a few designated threads, so the waits on
+// peers inside the kernels can be told apart from their work. Off (null) unless the measurement hook switches it on.
+__device__ unsigned long long* g_trace = nullptr;      // [0] = number of events so far, [1] = capacity, events from [2]
+__device__ __forceinline__ void trace_mark(unsigned long long tag) {
+  unsigned long long* tr = g_trace;
+  if (!tr) return;
+  const unsigned long long i = atomicAdd(tr, 1ull);
+  if (i < tr[1]) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    tr[2 + 2 * i] = tag;
+    tr[3 + 2 * i] = now;
+  }
+}
+// tags: kernel << 8 | phase.  kernel: 0x10 + column block = SpMV pass, 0x01 = update/push, 0x02 = scale/push (unlagged)
+#define LZ_TR(kernel, phase) (((unsigned)(kernel) << 8) | (unsigned)(phase))
+enum { TR_START = 1, TR_WAITED = 2, TR_PUSHED = 3, TR_END = 4, TR_SEND_START = 5, TR_SEND_END = 6 };
+
 struct lz_red_slot { double val; unsigned long long seq; };
 struct lz_red {
   lz_red_slot* area[LZ_MAX_WORLD];   // exchange area of every rank as seen from this GPU: [2 kinds][2][LZ_MAX_WORLD]
@@ -378,11 +396,20 @@ __global__ void __launch_bounds__(kBlock, NARROW ? 4 : 6) k_spmv_sell(const uint
   // every rank while the remaining CTAs gather from chunk blk. Senders never wait, gatherers wait only for data sent by
   // strictly earlier launches on every rank, so the scheme cannot deadlock whatever the CTA placement.
   if (blockIdx.x < job.nctas) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(LZ_TR(0x10 + blk, TR_SEND_START));
     push_chunk(job.src, job.peers, job.chunk, job.cl, world, job.rank, job.seq, job.ticket, blockIdx.x, job.nctas, &s_last);
+    if (s_last && threadIdx.x == 0) trace_mark(LZ_TR(0x10 + blk, TR_SEND_END));
+    if (threadIdx.x == 0 && g_trace && g_trace[1] >= 65536) {   // detailed mode: every sender CTA's end, with its SM id
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      trace_mark(LZ_TR(0x10 + blk, 8) | (smid << 16) | (blockIdx.x << 24));
+    }
     return;
   }
   const uint32_t cta = blockIdx.x - job.nctas, nctas = gridDim.x - job.nctas;
+  if (cta == 0 && threadIdx.x == 0) trace_mark(LZ_TR(0x10 + blk, TR_START));
   wait_chunk(flags, blk, world, wait_seq);
+  if (cta == 0 && threadIdx.x == 0) trace_mark(LZ_TR(0x10 + blk, TR_WAITED));
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t nwarps = nctas * kWarps;
   double d = 0.0;
@@ -524,8 +551,17 @@ __global__ void __launch_bounds__(kBlock, NARROW ? 4 : 6) k_spmv_sell(const uint
   if (final_pass) {
     d = block_sum(d, sm);
     grid_sum_finish(d, partials, ticket, alpha_out, sm, &s_last, cta, nctas, &red, 0, alpha_div);
+    if (s_last && threadIdx.x == 0) trace_mark(LZ_TR(0x10 + blk, TR_END));
+  } else if (cta == 0 && threadIdx.x == 0) {
+    trace_mark(LZ_TR(0x10 + blk, TR_END));   // CTA 0 only: indicative
+  }
+  if (threadIdx.x == 0 && g_trace && g_trace[1] >= 65536) {     // detailed mode: every gatherer CTA's end, with its SM id
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trace_mark(LZ_TR(0x10 + blk, 7) | (smid << 16) | ((unsigned long long)cta << 24));
   }
 }
+
 
 // --------------------------------------------------------------------------------------------- fused vector update
 // w <- (w - alpha q_j) - beta_prev q_prev, partial of ||w||^2. Same operation order as lanczos.cu:36-43.
@@ -663,8 +699,10 @@ __global__ void __launch_bounds__(kBlock) k_update_lagged_push(const double* __r
   __shared__ bool s_last;
   __shared__ double s_bcast;
   // ||u_j||^2 first (published one step ago), then alpha (the reduction this step waits for)
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(LZ_TR(0x01, TR_START));
   const double n2j = j ? red_consume_seq(red, 1, red.seq - 1, &s_bcast) : 1.0;
   const double a = red_consume_seq(red, 0, red.seq, &s_bcast) / n2j;
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(LZ_TR(0x01, TR_WAITED));
   const double nj = sqrt(n2j);
   const double rj = 1.0 / nj;
   const double cp = up ? nj / sqrt(norm2v[j - 1]) : 0.0;      // norm2v[j-1]: written by the previous launch of this kernel
@@ -706,6 +744,7 @@ __global__ void __launch_bounds__(kBlock) k_update_lagged_push(const double* __r
         push_ticket[c] = 0u;
         __threadfence_system();
         for (uint32_t r = 0; r < world; r++) st_release_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, push_seq);
+        trace_mark(LZ_TR(0x01, TR_PUSHED));
       }
     }
     __syncthreads();
@@ -740,6 +779,7 @@ __global__ void __launch_bounds__(kBlock) k_update_lagged_push(const double* __r
   }
   acc = block_sum(acc, sm);
   grid_sum_finish(acc, partials, ticket, nullptr, sm, &s_last, 0xFFFFFFFFu, 0, &red, 1);   // publishes the partial of ||u_{j+1}||^2
+  if (s_last && threadIdx.x == 0) trace_mark(LZ_TR(0x01, TR_END));
 }
 // Closes a lagged multi-GPU run: the last step has no update kernel, so its alpha and the last ||u||^2 are finished here.
 __global__ void k_lagged_finish(uint32_t j, double* __restrict__ norm2v, double* __restrict__ alpha_out, double* __restrict__ beta_out,
@@ -1254,7 +1294,7 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
     if (push_src && blk + 1 < c->ncolblk) {      // this pass also sends chunk blk + 1 of the vector being gathered
       for (int r = 0; r < LZ_MAX_WORLD; r++) { job.peers.x[r] = c->peer_xfull[r]; job.peers.f[r] = c->peer_flags[r]; }
       job.src = push_src; job.ticket = c->push_ticket; job.seq = wait_seq; job.cl = c->chunk_rows;
-      job.chunk = blk + 1; job.rank = (uint32_t)c->rank; job.nctas = (uint32_t)c->sm_count;
+      job.chunk = blk + 1; job.rank = (uint32_t)c->rank; job.nctas = c->push_ctas ? c->push_ctas : (uint32_t)c->sm_count / 4;   // 37 of 148: measured best at 8 GPUs (74: -4 %, 148: -10 %)
     }
     const int acc = blk > 0, fin = blk + 1 == c->ncolblk;
     // pass `blk` gathers from chunk `blk` of the gathered vector only: wait for exactly that piece of the all-gather
@@ -1265,6 +1305,9 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
       if (c->sell_group_force) group = c->sell_group_force;              // test knob (LZ_SELL_GROUP): small inputs through the quad paths
       const bool narrow = c->sell_narrow[blk] && group == 4;
       if (narrow && c->spmv_ctas_per_sm > 4) grid = (uint32_t)c->sm_count * 4;   // 64 registers: 4 resident CTAs per SM, one wave
+      // the sender CTAs of the fused exchange take resident slots: gatherers + senders must still fit in ONE wave, or the
+      // gatherers left over start when the first ones finish and the pass takes twice as long (measured at 8 GPUs: 205 vs 105 us)
+      if (job.nctas && grid > job.nctas + (uint32_t)c->sm_count) grid -= job.nctas;
       const uint32_t need = ((c->n_items + group - 1) / group + kWarps - 1) / kWarps;
       if (grid > need) grid = need;
       if (grid < 1) grid = 1;
@@ -1331,6 +1374,10 @@ int lz_k_update_lagged_push(lz_ctx* c, const double* t, const double* uj, const 
 int lz_k_lagged_finish(lz_ctx* c, uint32_t j, unsigned long long red_seq) {
   k_lagged_finish<<<1, 32, 0, c->stream>>>(j, c->norm2v, c->alpha, c->beta, make_red(c, red_seq));
   LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+int lz_k_set_trace(lz_ctx* c, unsigned long long* buf_device) {
+  LZ_CUDA(cudaMemcpyToSymbolAsync(g_trace, &buf_device, sizeof(buf_device), 0, cudaMemcpyHostToDevice, c->stream));
   return LZ_OK;
 }
 int lz_k_set_peer_timeout(lz_ctx* c, double seconds) {
