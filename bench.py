@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reorth-detail", action="store_true")
+    ap.add_argument("--no-f32-detail", action="store_true")
     ap.add_argument("--save-summary", default=None, help="write a summary fixture (.npz) of this run's answer (rank 0)")
     args = ap.parse_args()
 
@@ -382,6 +383,35 @@ def main():
                                        "note": "reorthogonalisation bytes over (reorth run - plain run) device time"}}
         detail["full_reorth"] = {"lanczos_ms": ms_r, "iters_per_s": k / (ms_r * 1e-3), "reorth_gbs": r_gbs}
 
+    # the same job with the basis stored in fp32 (LZ_BASIS_F32; one GPU): multOut and reorthogonalisation bytes halve
+    basis_f32 = None
+    if world == 1 and not args.no_f32_detail:
+        ctx.set_basis_precision(lz.BASIS_F32)
+        ctx.set_start_vector(None)
+        ctx.set_profiling(False)
+        for _ in range(2):
+            step()
+        ctx.timer_start()
+        for _ in range(3):
+            step()
+        ms32 = ctx.timer_stop() / 3.0
+        t32 = ctx.timings()
+        y32 = ctx.get_ans()
+        basis_f32 = {"value": k / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32, "multout_ms": t32.multout_ms,
+                     "multout_gbs": (4.0 * gi.n_local * k + 8.0 * gi.n_local) / (t32.multout_ms * 1e-3) / 1e9 if t32.multout_ms else None,
+                     "basis_bytes": 4.0 * gi.n_local * k}
+        if w.get("reorth") and not args.no_reorth_detail:
+            ctx.lanczos_run(k, lz.REORTH_FULL); ctx.sync()
+            ctx.timer_start()
+            for _ in range(3):
+                ctx.lanczos_run(k, lz.REORTH_FULL)
+            ms_r32 = ctx.timer_stop() / 3.0
+            b_r32 = 4.0 * gi.n_local * k * (k + 1) + 16.0 * gi.n_local * k
+            basis_f32["full_reorth"] = {"value": k / (ms_r32 * 1e-3), "unit": UNIT, "lanczos_ms": ms_r32, "reorth_algorithmic_gb": b_r32 / 1e9,
+                                        "reorth_gbs": b_r32 / max((ms_r32 - tm.lanczos_ms) * 1e-3, 1e-9) / 1e9}
+        ctx.set_basis_precision(lz.BASIS_F64)
+        ctx.set_start_vector(None)
+
     # end to end through the reference-facing call with HOST buffers (pinned), H2D of x and D2H of the answer inside
     x_host = torch.ones(n, dtype=torch.float64).pin_memory().numpy()
     y_host = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
@@ -428,6 +458,10 @@ def main():
     if rank == 0:
         if fix:
             parity = fp.compare(y_host, fix, alpha_g, beta_g, top_idx, top_val)
+            if basis_f32 is not None:
+                p32 = fp.compare(y32, fix)
+                basis_f32["parity_vs_reference_double"] = {"rel_2norm": p32["rel_2norm"], "top100_identical": p32["top100_identical"],
+                                                           "bar": "reference float vs double: 2.7e-7 .. 5.2e-6 (tests/golden/reference_float.npz)"}
             if "own_" in os.path.basename(fix):
                 parity["source"] = "this library's 1-GPU answer (the CPU reference cannot reach this size); " + parity["source"]
         else:
@@ -470,7 +504,7 @@ def main():
                 "impl_config": {"parallelism": f"row-sharded x{world}" if world > 1 else "single GPU", "exchange": exchange,
                                 "launch": "CUDA graph replay of the k-step loop" if graph_replay else "stream launches"},
                 "clocks": clocks, "e2e": e2e, "e2e_rank": e2e_rank, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "parity": parity, "result_finite": finite, "reorth_variant": reorth_variant, "detail": detail}
+                "parity": parity, "result_finite": finite, "reorth_variant": reorth_variant, "basis_f32": basis_f32, "detail": detail}
         print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()

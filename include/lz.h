@@ -110,6 +110,16 @@ int lz_csr_download(lz_ctx* ctx, uint32_t* row_offset_out, uint32_t* col_idx_out
 #define LZ_REORTH_FULL 1  /* every step, against all stored basis vectors: classical Gram-Schmidt, repeated when the first
                              pass removed more than half of ||w||^2 ("twice is enough", decided on the device)        */
 
+/* Storage precision of the Krylov basis V (call before lz_set_start_vector; changing it drops the start vector and any result).
+ *   LZ_BASIS_F64 (default): V in fp64, the graded precision (1e-9 parity with the reference's double path).
+ *   LZ_BASIS_F32: V in fp32 — half the bytes of every pass over the basis (multOut, full reorthogonalisation) and half its HBM
+ *     footprint. All arithmetic stays fp64 and the three-term recurrence runs on fp64 copies of the last vectors, so alpha/beta of a
+ *     plain run are those of the fp64 run; only the consumers of V see rounded vectors (error ~1e-8 relative, inside the 1e-6 the
+ *     reference's own float build agrees with its double build to). This is what lanczosDecomp<float> (cu_lanczos.cu:144) maps to.
+ *     One GPU per context only. */
+#define LZ_BASIS_F64 0
+#define LZ_BASIS_F32 1
+int lz_set_basis_precision(lz_ctx* ctx, int precision);
 /* x (n doubles, original order; NULL = all ones as in main.cu:79) -> device, computes ||x|| (cu_lanczos.h:18-24,63). */
 int lz_set_start_vector(lz_ctx* ctx, const double* x_host);
 /* Multi-GPU: only rank `root` reads x_host (one PCIe upload); the other ranks receive the vector over NVLink. Collective. */

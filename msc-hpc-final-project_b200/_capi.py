@@ -19,6 +19,7 @@ GRAPH_ER, GRAPH_RMAT, GRAPH_BAND = 1, 2, 3
 REORTH_NONE, REORTH_FULL = 0, 1
 EXCHANGE_NONE, EXCHANGE_NCCL, EXCHANGE_PEER_DENSE, EXCHANGE_PEER_SPARSE = 0, 1, 2, 3
 SPMV_AUTO, SPMV_VECTOR, SPMV_WARP = 0, 1, 2
+BASIS_F64, BASIS_F32 = 0, 1
 NCCL_UID_BYTES = 128
 
 
@@ -104,6 +105,7 @@ _sig("lz_set_start_vector_root", _ctx, _f64p, C.c_int)
 _sig("lz_spmv_host", _ctx, _f64p, _f64p)
 _sig("lz_get_basis", _ctx, C.c_uint32, _f64p)
 _sig("lz_set_spmv_variant", _ctx, C.c_int)
+_sig("lz_set_basis_precision", _ctx, C.c_int)
 _sig("lz_set_profiling", _ctx, C.c_int)
 _sig("lz_exchange_info", _ctx, _P(C.c_int), _P(C.c_double))
 _sig("lz_timings_get", _ctx, _P(Timings))
@@ -334,6 +336,9 @@ class Context:
         q = np.empty(self.graph_info().n)
         _check(lib.lz_get_basis(self._h, j, _f64(q)))
         return q
+
+    def set_basis_precision(self, p):
+        _check(lib.lz_set_basis_precision(self._h, p))
 
     def set_spmv_variant(self, v):
         _check(lib.lz_set_spmv_variant(self._h, v))

@@ -78,6 +78,9 @@ void free_vectors(lz_ctx* c) {
   cudaFree(c->flags); cudaFree(c->push_ticket); cudaFree(c->gfull);
   c->flags = nullptr; c->push_ticket = nullptr; c->gfull = nullptr;
   cudaFree(c->V); cudaFree(c->w); cudaFree(c->xfull); cudaFree(c->xstage); cudaFree(c->ans);
+  cudaFree(c->V32); cudaFree(c->q0_64);
+  for (double*& r : c->ring) { cudaFree(r); r = nullptr; }
+  c->V32 = nullptr; c->q0_64 = nullptr;
   cudaFree(c->alpha); cudaFree(c->beta); cudaFree(c->hcoef); cudaFree(c->eigvals); cudaFree(c->eigvecs); cudaFree(c->eigwork);
   cudaFree(c->coef); cudaFree(c->norm2v);
   c->norm2v = nullptr;
@@ -190,21 +193,44 @@ int ensure_graph_vectors(lz_ctx* c) {
   return LZ_OK;
 }
 
+// Row j of the Krylov basis as the fp64 vector the recurrence and the SpMV work on (fp32-basis mode: the ring), and as stored.
+inline double* vec64(lz_ctx* c, uint32_t j) { return c->basis_f32 ? c->ring[j % 3] : c->V + (uint64_t)j * c->ldv; }
+inline float* vec32(lz_ctx* c, uint32_t j) { return c->basis_f32 ? c->V32 + (uint64_t)j * c->ldv : nullptr; }
+inline const void* basis_ptr(const lz_ctx* c) { return c->basis_f32 ? (const void*)c->V32 : (const void*)c->V; }
+
 // Basis and k-sized arrays. Growing keeps row 0 (the start vector).
 int ensure_k(lz_ctx* c, uint32_t k) {
   LZ_TRY(ensure_graph_vectors(c));
   if (k <= c->k_cap) return LZ_OK;
-  double* nv = nullptr;
   LZ_CUDA(cudaStreamSynchronize(c->stream));
-  if (cudaMalloc((void**)&nv, (uint64_t)k * c->ldv * 8) != cudaSuccess) {
-    cudaGetLastError();
-    return lz_fail(LZ_ERR_ALLOC, "cannot allocate the Lanczos basis: %u x %llu doubles", k, (unsigned long long)c->ldv);
+  if (c->basis_f32) {
+    float* nv32 = nullptr;
+    if (cudaMalloc((void**)&nv32, (uint64_t)k * c->ldv * 4) != cudaSuccess) {
+      cudaGetLastError();
+      return lz_fail(LZ_ERR_ALLOC, "cannot allocate the fp32 Lanczos basis: %u x %llu floats", k, (unsigned long long)c->ldv);
+    }
+    LZ_CUDA(cudaMemsetAsync(nv32, 0, (uint64_t)k * c->ldv * 4, c->stream));
+    if (!c->q0_64) {
+      LZ_CUDA(cudaMalloc((void**)&c->q0_64, c->ldv * 8));
+      LZ_CUDA(cudaMemsetAsync(c->q0_64, 0, c->ldv * 8, c->stream));
+      for (double*& r : c->ring) { LZ_CUDA(cudaMalloc((void**)&r, c->ldv * 8)); LZ_CUDA(cudaMemsetAsync(r, 0, c->ldv * 8, c->stream)); }
+    }
+    if (c->V32 && c->have_x) LZ_CUDA(cudaMemcpyAsync(nv32, c->V32, c->ldv * 4, cudaMemcpyDeviceToDevice, c->stream));
+    LZ_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->V32);
+    c->V32 = nv32;
+  } else {
+    double* nv = nullptr;
+    if (cudaMalloc((void**)&nv, (uint64_t)k * c->ldv * 8) != cudaSuccess) {
+      cudaGetLastError();
+      return lz_fail(LZ_ERR_ALLOC, "cannot allocate the Lanczos basis: %u x %llu doubles", k, (unsigned long long)c->ldv);
+    }
+    LZ_CUDA(cudaMemsetAsync(nv, 0, (uint64_t)k * c->ldv * 8, c->stream));
+    if (c->V && c->have_x) LZ_CUDA(cudaMemcpyAsync(nv, c->V, c->ldv * 8, cudaMemcpyDeviceToDevice, c->stream));
+    LZ_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->V);
+    c->V = nv;
   }
-  LZ_CUDA(cudaMemsetAsync(nv, 0, (uint64_t)k * c->ldv * 8, c->stream));
-  if (c->V && c->have_x) LZ_CUDA(cudaMemcpyAsync(nv, c->V, c->ldv * 8, cudaMemcpyDeviceToDevice, c->stream));
-  LZ_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(c->V);
-  c->V = nv;
   // k-sized arrays: allocate the new set first, swap on success, so a failed cudaMalloc leaves a consistent (old) state
   double* fresh[8] = {};
   const size_t bytes[8] = {(size_t)(k + 1) * 8, (size_t)k * 8, (size_t)k * 8, (size_t)k * 8, (size_t)k * 8, (size_t)k * k * 8, (size_t)k * k * 8, (size_t)k * 8};
@@ -213,7 +239,7 @@ int ensure_k(lz_ctx* c, uint32_t k) {
       cudaGetLastError();
       for (int t = 0; t < i; t++) cudaFree(fresh[t]);
       // the basis already has k rows but the small arrays do not: fall back to "nothing allocated" rather than a half state
-      cudaFree(c->V); c->V = nullptr; c->k_cap = 0; c->have_x = false;
+      cudaFree(c->V); c->V = nullptr; cudaFree(c->V32); c->V32 = nullptr; c->k_cap = 0; c->have_x = false;
       c->have_tridiag = c->have_coef = c->have_ans = false;
       return lz_fail(LZ_ERR_ALLOC, "cannot allocate the k-sized work arrays for k = %u", k);
     }
@@ -323,6 +349,7 @@ static int create_body(lz_ctx* c, int device, int rank, int world, const void* u
   if (const char* e = getenv("LZ_SPMV_VARIANT")) { int v = atoi(e); if (v >= 0 && v <= LZ_SPMV_WARP) c->spmv_variant = v; }     // tuning knob
   if (const char* e = getenv("LZ_SPMV_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) c->spmv_ctas_per_sm = (uint32_t)v; }   // tuning knob
   if (const char* e = getenv("LZ_LAGGED_NORM")) c->lagged = atoi(e) != 0;
+  if (const char* e = getenv("LZ_BASIS")) c->basis_f32 = world == 1 && (e[0] == 'f' || e[0] == 'F') && strstr(e, "32") != nullptr;   // "f32": experiments
   if (const char* e = getenv("LZ_PUSH_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 1024) c->push_ctas = (uint32_t)v; }        // tuning knob
   if (const char* e = getenv("LZ_SELL_GROUP")) { int v = atoi(e); if (v == 1 || v == 4) c->sell_group_force = (uint32_t)v; }      // test knob
   // watchdog of the in-kernel waits on peers (seconds; 0 = none). A trap poisons the CUDA context: the ctx must be destroyed.
@@ -404,6 +431,25 @@ extern "C" int lz_sync(lz_ctx* c) {
   return LZ_OK;
 }
 
+extern "C" int lz_set_basis_precision(lz_ctx* c, int precision) {
+  if (!c || (precision != LZ_BASIS_F64 && precision != LZ_BASIS_F32)) return lz_fail(LZ_ERR_ARG, "bad basis precision");
+  if (precision == LZ_BASIS_F32 && c->world > 1) return lz_fail(LZ_ERR_ARG, "the fp32 basis (LZ_BASIS_F32) is implemented for one GPU per context only");
+  if ((precision == LZ_BASIS_F32) == c->basis_f32) return LZ_OK;
+  LZ_TRY(set_dev(c));
+  LZ_CUDA(cudaStreamSynchronize(c->stream));
+  drop_graph(c);
+  // the basis and the start vector are re-created in the new precision by the next lz_set_start_vector
+  cudaFree(c->V); c->V = nullptr; cudaFree(c->V32); c->V32 = nullptr;
+  cudaFree(c->q0_64); c->q0_64 = nullptr;
+  for (double*& r : c->ring) { cudaFree(r); r = nullptr; }
+  c->k_cap = 0;
+  c->epoch++;
+  c->basis_f32 = precision == LZ_BASIS_F32;
+  c->have_x = c->have_tridiag = c->have_coef = c->have_ans = false;
+  c->lagged_done = false;
+  return LZ_OK;
+}
+
 extern "C" int lz_set_spmv_variant(lz_ctx* c, int variant) {
   if (!c || variant < 0 || variant > LZ_SPMV_WARP) return lz_fail(LZ_ERR_ARG, "bad SpMV variant");
   c->spmv_variant = variant;
@@ -431,11 +477,13 @@ static int set_start_vector_impl(lz_ctx* c, const double* x_host, int root) {
     LZ_TRY(lz_k_fill(c, c->xstage, c->n, 1.0));   // all ones, as every reference driver uses (main.cu:79)
   }
   LZ_TRY(lz_k_norm2(c, c->xstage, c->n, c->scal + 2));
+  double* q0 = c->basis_f32 ? c->q0_64 : c->V;
   if (c->world > 1) {
-    LZ_TRY(lz_k_permute_in_local(c, c->xstage, c->scal + 2, c->V));   // own rows only; the gathered vector is filled by the run
+    LZ_TRY(lz_k_permute_in_local(c, c->xstage, c->scal + 2, q0));   // own rows only; the gathered vector is filled by the run
   } else {
-    LZ_TRY(lz_k_permute_in(c, c->xstage, c->scal + 2, 0, c->n_loc, c->V));
+    LZ_TRY(lz_k_permute_in(c, c->xstage, c->scal + 2, 0, c->n_loc, q0));
   }
+  if (c->basis_f32) LZ_TRY(lz_k_convert(c, q0, c->V32, nullptr, nullptr, c->n_loc));
   c->have_x = true;
   c->have_tridiag = c->have_coef = c->have_ans = false;
   return LZ_OK;
@@ -452,8 +500,9 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
     // Lagged normalisation: 2 SpMV passes + ONE vector kernel per step; row j >= 1 of V keeps u_j unnormalised with
     // norm2v[j] = ||u_j||^2 (row 0 is the normalised start vector). See k_update_lagged.
     LZ_TRY(lz_k_fill(c, c->norm2v, 1, 1.0));
+    if (c->basis_f32) LZ_CUDA(cudaMemcpyAsync(c->ring[0], c->q0_64, ldv * 8, cudaMemcpyDeviceToDevice, c->stream));
     for (uint32_t j = 0; j < k; j++) {
-      double* uj = c->V + (uint64_t)j * ldv;
+      double* uj = vec64(c, j);
       {  // t = A u_j ; alpha_j = (t . u_j) / ||u_j||^2
         Scope s(c, 0);
         LZ_TRY(lz_k_spmv_dot(c, uj, uj, c->w, c->alpha + j, 0ull, nullptr, 0ull, c->norm2v + j));
@@ -461,8 +510,8 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
       if (j + 1 == k) break;
       {  // u_{j+1} = t/||u_j|| - alpha_j q_j - beta_{j-1} q_{j-1} ; ||u_{j+1}||^2 ; beta_j
         Scope s(c, 1);
-        LZ_TRY(lz_k_update_lagged(c, c->w, uj, j ? uj - ldv : nullptr, c->alpha + j, c->norm2v + j, j ? c->norm2v + (j - 1) : nullptr,
-                                  uj + ldv, c->norm2v + (j + 1), c->beta + j));
+        LZ_TRY(lz_k_update_lagged(c, c->w, uj, j ? vec64(c, j - 1) : nullptr, c->alpha + j, c->norm2v + j, j ? c->norm2v + (j - 1) : nullptr,
+                                  vec64(c, j + 1), c->norm2v + (j + 1), c->beta + j, vec32(c, j + 1)));
       }
     }
     return LZ_OK;
@@ -499,8 +548,11 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
       LZ_TRY(allgather_chunks(c, c->xfull, true));
     }
   }
+  if (c->basis_f32) LZ_CUDA(cudaMemcpyAsync(c->ring[0], c->q0_64, ldv * 8, cudaMemcpyDeviceToDevice, c->stream));
   for (uint32_t j = 0; j < k; j++) {
-    double* qj = c->V + (uint64_t)j * ldv;
+    double* qj = vec64(c, j);
+    double* qprev = j ? vec64(c, j - 1) : nullptr;
+    double* qnext = vec64(c, j + 1 < k ? j + 1 : j);
     {  // w = A q_j ; alpha_j = w . q_j                                   (cu_lanczos.cu:101-105)
       Scope s(c, 0);
       const bool last = j + 1 == k;    // the last alpha is read by nobody on the device: reduce it with NCCL into alpha[k-1]
@@ -515,7 +567,7 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
     {  // w -= alpha_j q_j ; w -= beta_{j-1} q_{j-1} ; ||w||^2             (cu_lanczos.cu:108-120)
       Scope s(c, 1);
       const unsigned long long a_seq = peer_scalars ? c->red_seq : 0ull;   // consumes alpha (kind 0, a_seq), publishes ||w||^2 (kind 1, a_seq)
-      LZ_TRY(lz_k_update_norm(c, c->w, qj, j ? qj - ldv : nullptr, c->alpha + j, j ? c->beta + (j - 1) : nullptr,
+      LZ_TRY(lz_k_update_norm(c, c->w, qj, qprev, c->alpha + j, j ? c->beta + (j - 1) : nullptr,
                               reorth ? c->scal + 3 : c->scal + 1, a_seq));
     }
     if (reorth) {
@@ -524,23 +576,23 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
       Scope s(c, 3);
       int* skip = c->status + 1;
       LZ_TRY(allreduce_sum(c, c->scal + 3, 1));                                   // ||w||^2 before
-      LZ_TRY(lz_k_multidot(c, c->V, j + 1, c->w, c->hcoef));
+      LZ_TRY(lz_k_multidot(c, basis_ptr(c), c->basis_f32, j + 1, c->w, c->hcoef));
       LZ_TRY(allreduce_sum(c, c->hcoef, j + 1));
-      LZ_TRY(lz_k_combine(c, c->V, j + 1, c->hcoef, -1.0, c->w, c->w, c->scal + 1));
+      LZ_TRY(lz_k_combine(c, basis_ptr(c), c->basis_f32, j + 1, c->hcoef, -1.0, c->w, c->w, c->scal + 1));
       LZ_TRY(allreduce_sum(c, c->scal + 1, 1));                                   // ||w||^2 after pass 1
       LZ_TRY(lz_k_reorth_decide(c, c->scal + 3, c->scal + 1, skip, reinterpret_cast<unsigned int*>(c->status + 2)));
-      LZ_TRY(lz_k_multidot(c, c->V, j + 1, c->w, c->hcoef, skip));
+      LZ_TRY(lz_k_multidot(c, basis_ptr(c), c->basis_f32, j + 1, c->w, c->hcoef, skip));
       LZ_TRY(allreduce_sum(c, c->hcoef, j + 1));
-      LZ_TRY(lz_k_combine(c, c->V, j + 1, c->hcoef, -1.0, c->w, c->w, c->scal + 4, skip));
+      LZ_TRY(lz_k_combine(c, basis_ptr(c), c->basis_f32, j + 1, c->hcoef, -1.0, c->w, c->w, c->scal + 4, skip));
       LZ_TRY(allreduce_sum(c, c->scal + 4, 1));
       LZ_TRY(lz_k_reorth_select(c, skip, c->scal + 4, c->scal + 1));
     }
     if (!peer_scalars && !reorth) LZ_TRY(allreduce_sum(c, c->scal + 1, 1));
     {  // beta_j = ||w|| ; q_{j+1} = w / beta_j                            (cu_lanczos.cu:120-123)
       Scope s(c, 1);
-      if (c->peer_push) LZ_TRY(lz_k_scale_push(c, c->w, c->scal + 1, qj + ldv, c->beta + j, ++c->push_seq, fused_push ? 1u : c->ncolblk,
+      if (c->peer_push) LZ_TRY(lz_k_scale_push(c, c->w, c->scal + 1, qnext, c->beta + j, ++c->push_seq, fused_push ? 1u : c->ncolblk,
                                                peer_scalars ? c->red_seq : 0ull));
-      else LZ_TRY(lz_k_scale(c, c->w, c->scal + 1, qj + ldv, dist ? c->xfull : nullptr, c->beta + j));
+      else LZ_TRY(lz_k_scale(c, c->w, c->scal + 1, qnext, dist ? c->xfull : nullptr, c->beta + j, vec32(c, j + 1)));
     }
     if (!c->peer_push) LZ_TRY(allgather_chunks(c, c->xfull, true));
   }
@@ -559,6 +611,7 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
   if (reorth != LZ_REORTH_NONE && reorth != LZ_REORTH_FULL) return lz_fail(LZ_ERR_ARG, "bad reorth mode %d", reorth);
   if (!c->have_x) return lz_fail(LZ_ERR_ARG, "lz_set_start_vector must be called before lz_lanczos_run");
   LZ_TRY(set_dev(c));
+  if (c->basis_f32 && c->world > 1) return lz_fail(LZ_ERR_ARG, "the fp32 basis (LZ_BASIS_F32) is implemented for one GPU per context only");
   LZ_TRY(ensure_k(c, k));
   // chunk 0 of each new vector is sent by the normalisation kernel, chunk b + 1 by SpMV pass b (sliced variant only)
   bool fused_push = c->peer_push && !c->sparse_push && c->spmv_variant == LZ_SPMV_AUTO && c->ncolblk > 1;
@@ -588,7 +641,7 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
   bool done = false;
   if (use_graph) {
     const bool hit = c->graph_exec && c->graph_k == k && c->graph_reorth == reorth && c->graph_variant == c->spmv_variant &&
-                     c->graph_V == c->V && c->graph_epoch == c->epoch;
+                     c->graph_V == (const double*)basis_ptr(c) && c->graph_epoch == c->epoch;
     if (!hit) {
       drop_graph(c);
       const uint32_t launches0 = c->launches;
@@ -597,7 +650,7 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
         const int rc = enqueue_steps(c, k, reorth, fused_push, peer_scalars);
         const cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
         if (rc == LZ_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&c->graph_exec, g, 0) == cudaSuccess) {
-          c->graph_k = k; c->graph_reorth = reorth; c->graph_variant = c->spmv_variant; c->graph_V = c->V; c->graph_epoch = c->epoch;
+          c->graph_k = k; c->graph_reorth = reorth; c->graph_variant = c->spmv_variant; c->graph_V = (double*)basis_ptr(c); c->graph_epoch = c->epoch;
           c->graph_launches = c->launches - launches0;
         } else {
           c->graph_exec = nullptr;
@@ -761,7 +814,7 @@ extern "C" int lz_multout(lz_ctx* c) {
     LZ_TRY(lz_k_coef_scale(c, c->coef, c->norm2v, c->k_done, c->hcoef));
     coef = c->hcoef;
   }
-  LZ_TRY(lz_k_combine(c, c->V, c->k_done, coef, 1.0, nullptr, c->ans, nullptr));
+  LZ_TRY(lz_k_combine(c, basis_ptr(c), c->basis_f32, c->k_done, coef, 1.0, nullptr, c->ans, nullptr));
   LZ_CUDA(cudaEventRecord(c->ev_m1, c->stream));
   c->have_ans = true;
   return LZ_OK;
@@ -839,7 +892,9 @@ extern "C" int lz_get_basis(lz_ctx* c, uint32_t j, double* q_host) {
   if (!c->have_x || j >= (c->have_tridiag ? c->k_done : 1u)) return lz_fail(LZ_ERR_ARG, "basis vector %u not available", j);
   LZ_TRY(set_dev(c));
   // after a lagged-normalisation run rows 1.. hold u_j = ||u_j|| q_j
-  return gather_to_host(c, c->V + (uint64_t)j * c->ldv, q_host, (c->lagged_done && c->have_tridiag && j > 0) ? c->norm2v + j : nullptr);
+  const double* row = c->basis_f32 ? c->w : c->V + (uint64_t)j * c->ldv;
+  if (c->basis_f32) LZ_TRY(lz_k_convert(c, nullptr, nullptr, c->V32 + (uint64_t)j * c->ldv, c->w, c->n_loc));   // w is scratch between runs
+  return gather_to_host(c, row, q_host, (c->lagged_done && c->have_tridiag && j > 0) ? c->norm2v + j : nullptr);
 }
 
 extern "C" int lz_set_profiling(lz_ctx* c, int on) {

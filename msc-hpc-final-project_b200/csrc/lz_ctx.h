@@ -133,7 +133,14 @@ struct lz_ctx {
   uint32_t k_cap = 0;              // rows allocated in V
   uint32_t k_done = 0;             // steps of the last run
   int reorth_done = 0;
-  double* V = nullptr;             // device, [k_cap][ldv] basis, vector-contiguous (parallel-mult-on-card layout)
+  double* V = nullptr;             // device, [k_cap][ldv] basis, vector-contiguous (parallel-mult-on-card layout); null in fp32-basis mode
+  // fp32-basis mode (LZ_BASIS_F32): the basis is stored as floats; the recurrence itself runs on a ring of three fp64 vectors
+  // (u_{j-1}, u_j, u_{j+1}) plus the fp64 start vector, so alpha/beta are those of the fp64 run and only the consumers of V
+  // (full reorthogonalisation, multOut, lz_get_basis) see rounded vectors.
+  bool basis_f32 = false;
+  float* V32 = nullptr;            // device, [k_cap][ldv]
+  double* ring[3] = {};            // device, [ldv] each
+  double* q0_64 = nullptr;         // device, [ldv] normalised start vector
   double* w = nullptr;             // device, [n_loc]
   double* xfull = nullptr;         // device, [n_loc * world] gathered Krylov vector (world > 1), else unused
   double* xstage = nullptr;        // device, [n] staging for host vectors in original order
@@ -198,7 +205,9 @@ int lz_k_spmv_dot(lz_ctx* c, const double* x_gather, const double* q_local, doub
                   const double* alpha_div = nullptr /* device scalar: alpha_out = (w . q) / *alpha_div (lagged normalisation) */);
 // lagged normalisation (one GPU, plain recurrence): see k_update_lagged
 int lz_k_update_lagged(lz_ctx* c, const double* t, const double* uj, const double* uprev, const double* alpha, const double* norm2_j,
-                       const double* norm2_prev, double* u_next, double* norm2_out, double* beta_out);
+                       const double* norm2_prev, double* u_next, double* norm2_out, double* beta_out, float* u32_next = nullptr);
+// dst32 != null: dst32 = (float)src64 ; else dst64 = (double)src32
+int lz_k_convert(lz_ctx* c, const double* src64, float* dst32, const float* src32, double* dst64, uint64_t n);
 // lagged normalisation on several GPUs (peer exchange + peer scalars): see k_update_lagged_push
 int lz_k_update_lagged_push(lz_ctx* c, const double* t, const double* uj, const double* uprev, double* u_next, uint32_t j,
                             unsigned long long push_seq, uint32_t push_chunks, unsigned long long red_seq);
@@ -210,7 +219,7 @@ int lz_k_div_sqrt(lz_ctx* c, double* v, uint64_t n, const double* norm2);
 int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev, double* alpha, const double* beta_prev,
                      double* norm2_out /* device scalar or null */, unsigned long long red_seq = 0 /* > 0: scalars go through the peer exchange */);
 // q_next = w / sqrt(*norm2); when xfull != null also stores it into this rank's slots of the chunk-major gathered vector
-int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* xfull, double* beta_out);
+int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* xfull, double* beta_out, float* q32_next = nullptr);
 // peer exchange: q_next = w / sqrt(*norm2) (norm2 == null: plain copy of w) stored locally and into every rank's gathered vector; raises seq
 int lz_k_scale_push(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* beta_out, unsigned long long seq,
                     uint32_t push_chunks /* chunks [0, push_chunks) are sent here; the rest by the SpMV passes */,
@@ -221,8 +230,9 @@ int lz_k_permute_in_local(lz_ctx* c, const double* x_orig, const double* norm2, 
 int lz_k_spread(lz_ctx* c, const double* local, double* xfull);
 int lz_k_collect(lz_ctx* c, const double* xfull, double* local);
 int lz_k_norm2(lz_ctx* c, const double* v, uint64_t len, double* out);
-int lz_k_multidot(lz_ctx* c, const double* V, uint32_t nvec, const double* w, double* h_out /* device [nvec] */, const int* skip = nullptr);
-int lz_k_combine(lz_ctx* c, const double* V, uint32_t nvec, const double* coef, double coef_sign, const double* base, double* out,
+// V: the basis, [nvec][ldv] doubles, or floats when f32 (LZ_BASIS_F32)
+int lz_k_multidot(lz_ctx* c, const void* V, bool f32, uint32_t nvec, const double* w, double* h_out /* device [nvec] */, const int* skip = nullptr);
+int lz_k_combine(lz_ctx* c, const void* V, bool f32, uint32_t nvec, const double* coef, double coef_sign, const double* base, double* out,
                  double* norm2_out /* device scalar or null */, const int* skip = nullptr);
 int lz_k_reorth_decide(lz_ctx* c, const double* norm2_before, const double* norm2_after, int* skip, unsigned int* second_passes);
 int lz_k_reorth_select(lz_ctx* c, const int* skip, const double* norm2_second, double* norm2);

@@ -122,6 +122,16 @@ __device__ __forceinline__ double red_consume(const lz_red& red, int kind, doubl
   return red_consume_seq(red, kind, red.seq, sm_bcast);
 }
 
+// Basis storage: fp64, or fp32 (LZ_BASIS_F32: half the bytes of every pass over V; all arithmetic stays fp64).
+template <class TV> __device__ __forceinline__ double2 ld_pair(const TV* base, uint64_t i2);
+template <> __device__ __forceinline__ double2 ld_pair<double>(const double* base, uint64_t i2) {
+  return __ldcs(reinterpret_cast<const double2*>(base) + i2);
+}
+template <> __device__ __forceinline__ double2 ld_pair<float>(const float* base, uint64_t i2) {
+  const float2 f = __ldcs(reinterpret_cast<const float2*>(base) + i2);
+  return make_double2((double)f.x, (double)f.y);
+}
+
 // Deterministic grid reduction tail. Thread 0 of every CTA passes its CTA value; the last CTA to arrive sums all
 // `gridDim.x` partials in index order (strided per thread, then a fixed tree) and stores op(sum) to *out.
 __device__ __forceinline__ void grid_sum_finish(double cta_val, double* partials, unsigned int* ticket, double* out, double* sm,
@@ -625,7 +635,8 @@ __device__ __forceinline__ double lagged_entry(double t, double q, double p, dou
 __global__ void __launch_bounds__(kBlock) k_update_lagged(const double* __restrict__ t, const double* __restrict__ uj, const double* __restrict__ up,
                                                           const double* __restrict__ alpha_p, const double* __restrict__ norm2_j,
                                                           const double* __restrict__ norm2_p, uint64_t n, double* __restrict__ u_next,
-                                                          double* partials, unsigned int* ticket, double* norm2_out, double* beta_out) {
+                                                          double* partials, unsigned int* ticket, double* norm2_out, double* beta_out,
+                                                          float* __restrict__ u32_next /* fp32 basis row, or null */) {
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
   // u_{j+1} = (t - alpha u_j) / ||u_j|| - (||u_j|| / ||u_{j-1}||) u_{j-1}: the two scalars are formed once per thread, so the
@@ -647,12 +658,14 @@ __global__ void __launch_bounds__(kBlock) k_update_lagged(const double* __restri
     v.x = lagged_entry(tv.x, qv.x, pv.x, a, rj, cp, up != nullptr);
     v.y = lagged_entry(tv.y, qv.y, pv.y, a, rj, cp, up != nullptr);
     o2[i] = v;
+    if (u32_next) reinterpret_cast<float2*>(u32_next)[i] = make_float2((float)v.x, (float)v.y);
     acc = fma(v.x, v.x, acc);
     acc = fma(v.y, v.y, acc);
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const double v = lagged_entry(t[n - 1], uj[n - 1], up ? up[n - 1] : 0.0, a, rj, cp, up != nullptr);
     u_next[n - 1] = v;
+    if (u32_next) u32_next[n - 1] = (float)v;
     acc = fma(v, v, acc);
   }
   acc = block_sum(acc, sm);
@@ -813,7 +826,7 @@ __device__ __forceinline__ uint64_t xfull_index(uint64_t l, uint64_t cl, uint32_
 // vector; beta_out = sqrt(norm2). n and cl are even, so a double2 never straddles a chunk.
 __global__ void __launch_bounds__(kBlock) k_scale(const double* __restrict__ w, const double* __restrict__ norm2_p, uint64_t n,
                                                   double* __restrict__ q_next, double* __restrict__ xfull, uint64_t cl, uint32_t world,
-                                                  uint32_t rank, double* beta_out) {
+                                                  uint32_t rank, double* beta_out, float* __restrict__ q32_next) {
   const double beta = sqrt(*norm2_p);
   if (blockIdx.x == 0 && threadIdx.x == 0 && beta_out) *beta_out = beta;
   const uint64_t n2 = n >> 1;
@@ -824,8 +837,21 @@ __global__ void __launch_bounds__(kBlock) k_scale(const double* __restrict__ w, 
     v.x /= beta;
     v.y /= beta;
     q2[i] = v;
+    if (q32_next) reinterpret_cast<float2*>(q32_next)[i] = make_float2((float)v.x, (float)v.y);
     if (xfull) *reinterpret_cast<double2*>(xfull + xfull_index(2 * i, cl, world, rank)) = v;
   }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {      // odd tail (n_loc is a multiple of 32 in practice)
+    const double v = w[n - 1] / beta;
+    q_next[n - 1] = v;
+    if (q32_next) q32_next[n - 1] = (float)v;
+  }
+}
+// dst32[i] = (float)src[i]
+__global__ void __launch_bounds__(kBlock) k_to_f32(const double* __restrict__ src, float* __restrict__ dst, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kBlock) dst[i] = (float)src[i];
+}
+__global__ void __launch_bounds__(kBlock) k_to_f64(const float* __restrict__ src, double* __restrict__ dst, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kBlock) dst[i] = (double)src[i];
 }
 
 // Producer side of the peer exchange, fused into the normalisation: q_next = w / beta is stored locally and, 16 bytes at a
@@ -984,7 +1010,8 @@ __global__ void k_permute_out(const double* __restrict__ y_new, const uint32_t* 
 // h[t] = sum_i V[t][i] w[i], t < nvec. Vectors are processed in register tiles of TILE so w is re-read nvec/TILE times
 // (+1/TILE traffic) while TILE independent 16-byte loads per thread are in flight.
 constexpr int kDotTile = 8;
-__global__ void __launch_bounds__(kBlock) k_multidot(const double* __restrict__ V, uint64_t ldv, uint32_t nvec, const double* __restrict__ w,
+template <class TV>
+__global__ void __launch_bounds__(kBlock) k_multidot(const TV* __restrict__ V, uint64_t ldv, uint32_t nvec, const double* __restrict__ w,
                                                      uint64_t n, double* partials /* [nvec][grid] */, unsigned int* ticket, double* h_out,
                                                      const int* __restrict__ skip) {
   __shared__ double sm[kWarps];
@@ -997,14 +1024,14 @@ __global__ void __launch_bounds__(kBlock) k_multidot(const double* __restrict__ 
 #pragma unroll
     for (int u = 0; u < kDotTile; u++) acc[u] = 0.0;
     const uint32_t nt = min((uint32_t)kDotTile, nvec - t0);
-    const double2* v2 = reinterpret_cast<const double2*>(V + (uint64_t)t0 * ldv);
+    const TV* vb = V + (uint64_t)t0 * ldv;
     const uint64_t ld2 = ldv >> 1;
     if (nt == kDotTile) {
       for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
         const double2 wv = w2[i];
         double2 vv[kDotTile];
 #pragma unroll
-        for (int u = 0; u < kDotTile; u++) vv[u] = __ldcs(v2 + (uint64_t)u * ld2 + i);
+        for (int u = 0; u < kDotTile; u++) vv[u] = ld_pair<TV>(vb, (uint64_t)u * ld2 + i);
 #pragma unroll
         for (int u = 0; u < kDotTile; u++) { acc[u] += vv[u].x * wv.x; acc[u] += vv[u].y * wv.y; }
       }
@@ -1013,13 +1040,13 @@ __global__ void __launch_bounds__(kBlock) k_multidot(const double* __restrict__ 
         const double2 wv = w2[i];
 #pragma unroll
         for (int u = 0; u < kDotTile; u++)
-          if (u < (int)nt) { const double2 vv = __ldcs(v2 + (uint64_t)u * ld2 + i); acc[u] += vv.x * wv.x; acc[u] += vv.y * wv.y; }
+          if (u < (int)nt) { const double2 vv = ld_pair<TV>(vb, (uint64_t)u * ld2 + i); acc[u] += vv.x * wv.x; acc[u] += vv.y * wv.y; }
       }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
 #pragma unroll
       for (int u = 0; u < kDotTile; u++)
-        if (u < (int)nt) acc[u] += V[(uint64_t)(t0 + u) * ldv + n - 1] * w[n - 1];
+        if (u < (int)nt) acc[u] += (double)V[(uint64_t)(t0 + u) * ldv + n - 1] * w[n - 1];
     }
 #pragma unroll
     for (int u = 0; u < kDotTile; u++) {
@@ -1052,7 +1079,8 @@ __global__ void __launch_bounds__(kBlock) k_multidot(const double* __restrict__ 
 // ---------------------------------------------------------------------------- tall-skinny GEMV-N (reorth update, multOut)
 // out[i] = (base ? base[i] : 0) + sign * sum_t coef[t] V[t][i], accumulated in t order (the order of the reference's
 // row-major Trans dgemv, multiplyOut.cu:44). Optional partial of ||out||^2.
-__global__ void __launch_bounds__(kBlock) k_combine(const double* __restrict__ V, uint64_t ldv, uint32_t nvec, const double* __restrict__ coef,
+template <class TV>
+__global__ void __launch_bounds__(kBlock) k_combine(const TV* __restrict__ V, uint64_t ldv, uint32_t nvec, const double* __restrict__ coef,
                                                     double sign, const double* base, double* out, uint64_t n, double* partials,
                                                     unsigned int* ticket, double* norm2_out, const int* __restrict__ skip) {
   extern __shared__ double s_coef[];
@@ -1062,7 +1090,6 @@ __global__ void __launch_bounds__(kBlock) k_combine(const double* __restrict__ V
   for (uint32_t t = threadIdx.x; t < nvec; t += kBlock) s_coef[t] = sign * coef[t];
   __syncthreads();
   const uint64_t n2 = n >> 1, ld2 = ldv >> 1;
-  const double2* v2 = reinterpret_cast<const double2*>(V);
   const double2* b2 = reinterpret_cast<const double2*>(base);
   double2* o2 = reinterpret_cast<double2*>(out);
   double nacc = 0.0;
@@ -1072,12 +1099,12 @@ __global__ void __launch_bounds__(kBlock) k_combine(const double* __restrict__ V
     for (; t + 8 <= nvec; t += 8) {
       double2 vv[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) vv[u] = __ldcs(v2 + (uint64_t)(t + u) * ld2 + i);
+      for (int u = 0; u < 8; u++) vv[u] = ld_pair<TV>(V, (uint64_t)(t + u) * ld2 + i);
 #pragma unroll
       for (int u = 0; u < 8; u++) { acc.x += s_coef[t + u] * vv[u].x; acc.y += s_coef[t + u] * vv[u].y; }
     }
     for (; t < nvec; t++) {
-      const double2 vv = __ldcs(v2 + (uint64_t)t * ld2 + i);
+      const double2 vv = ld_pair<TV>(V, (uint64_t)t * ld2 + i);
       acc.x += s_coef[t] * vv.x;
       acc.y += s_coef[t] * vv.y;
     }
@@ -1087,7 +1114,7 @@ __global__ void __launch_bounds__(kBlock) k_combine(const double* __restrict__ V
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     double acc = base ? base[n - 1] : 0.0;
-    for (uint32_t t = 0; t < nvec; t++) acc += s_coef[t] * V[(uint64_t)t * ldv + n - 1];
+    for (uint32_t t = 0; t < nvec; t++) acc += s_coef[t] * (double)V[(uint64_t)t * ldv + n - 1];
     out[n - 1] = acc;
     nacc += acc * acc;
   }
@@ -1345,11 +1372,11 @@ int lz_k_update_norm(lz_ctx* c, double* w, const double* qj, const double* qprev
 }
 
 int lz_k_update_lagged(lz_ctx* c, const double* t, const double* uj, const double* uprev, const double* alpha, const double* norm2_j,
-                       const double* norm2_prev, double* u_next, double* norm2_out, double* beta_out) {
+                       const double* norm2_prev, double* u_next, double* norm2_out, double* beta_out, float* u32_next) {
   unsigned g = stream_grid(c, c->n_loc / 2 + 1);
   LZ_TRY(ensure_partials(c, g));
   k_update_lagged<<<g, kBlock, 0, c->stream>>>(t, uj, uprev, alpha, norm2_j, norm2_prev, c->n_loc, u_next, c->partials, c->ticket + 1,
-                                               norm2_out, beta_out);
+                                               norm2_out, beta_out, u32_next);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
@@ -1396,9 +1423,15 @@ int lz_k_div_sqrt(lz_ctx* c, double* v, uint64_t n, const double* norm2) {
   return LZ_OK;
 }
 
-int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* xfull, double* beta_out) {
+int lz_k_convert(lz_ctx* c, const double* src64, float* dst32, const float* src32, double* dst64, uint64_t n) {
+  if (dst32) k_to_f32<<<stream_grid(c, n), kBlock, 0, c->stream>>>(src64, dst32, n);
+  else k_to_f64<<<stream_grid(c, n), kBlock, 0, c->stream>>>(src32, dst64, n);
+  LZ_LAUNCH_CHECK();
+  return LZ_OK;
+}
+int lz_k_scale(lz_ctx* c, const double* w, const double* norm2, double* q_next, double* xfull, double* beta_out, float* q32_next) {
   unsigned g = stream_grid(c, c->n_loc / 2 + 1);
-  k_scale<<<g, kBlock, 0, c->stream>>>(w, norm2, c->n_loc, q_next, xfull, c->chunk_rows, (uint32_t)c->world, (uint32_t)c->rank, beta_out);
+  k_scale<<<g, kBlock, 0, c->stream>>>(w, norm2, c->n_loc, q_next, xfull, c->chunk_rows, (uint32_t)c->world, (uint32_t)c->rank, beta_out, q32_next);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
@@ -1458,22 +1491,25 @@ int lz_k_norm2(lz_ctx* c, const double* v, uint64_t len, double* out) {
   return LZ_OK;
 }
 
-int lz_k_multidot(lz_ctx* c, const double* V, uint32_t nvec, const double* w, double* h_out, const int* skip) {
+int lz_k_multidot(lz_ctx* c, const void* V, bool f32, uint32_t nvec, const double* w, double* h_out, const int* skip) {
   unsigned g = (unsigned)c->sm_count * 4;
   uint64_t want = (c->n_loc / 2 + kBlock) / kBlock;
   if (want < g) g = (unsigned)(want ? want : 1);
   LZ_TRY(ensure_partials(c, (uint64_t)g * nvec));
-  k_multidot<<<g, kBlock, 0, c->stream>>>(V, c->ldv, nvec, w, c->n_loc, c->partials, c->ticket + 3, h_out, skip);
+  if (f32) k_multidot<float><<<g, kBlock, 0, c->stream>>>((const float*)V, c->ldv, nvec, w, c->n_loc, c->partials, c->ticket + 3, h_out, skip);
+  else k_multidot<double><<<g, kBlock, 0, c->stream>>>((const double*)V, c->ldv, nvec, w, c->n_loc, c->partials, c->ticket + 3, h_out, skip);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
 
-int lz_k_combine(lz_ctx* c, const double* V, uint32_t nvec, const double* coef, double coef_sign, const double* base, double* out,
+int lz_k_combine(lz_ctx* c, const void* V, bool f32, uint32_t nvec, const double* coef, double coef_sign, const double* base, double* out,
                  double* norm2_out, const int* skip) {
   unsigned g = stream_grid(c, c->n_loc / 2 + 1);
   LZ_TRY(ensure_partials(c, g));
-  k_combine<<<g, kBlock, nvec * sizeof(double), c->stream>>>(V, c->ldv, nvec, coef, coef_sign, base, out, c->n_loc, c->partials,
-                                                             c->ticket + 4, norm2_out, skip);
+  if (f32) k_combine<float><<<g, kBlock, nvec * sizeof(double), c->stream>>>((const float*)V, c->ldv, nvec, coef, coef_sign, base, out, c->n_loc,
+                                                                             c->partials, c->ticket + 4, norm2_out, skip);
+  else k_combine<double><<<g, kBlock, nvec * sizeof(double), c->stream>>>((const double*)V, c->ldv, nvec, coef, coef_sign, base, out, c->n_loc,
+                                                                          c->partials, c->ticket + 4, norm2_out, skip);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }

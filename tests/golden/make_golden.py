@@ -80,5 +80,25 @@ def main():
               f"final-vs-arnoldi={rel_arn:.2e} top100 gap={oracle.top_gap(ans):.2e}")
 
 
+def main_float():
+    """Single-precision goldens: the reference's own float instantiation (lanczosDecomp<float> -> eigenDecomp<float> ->
+    multOut<float>, cu_lanczos.cu:144 / README.md:21) on two of the graphs above, stored as float32 next to the distance
+    between the reference's float and double answers — the bar our fp32-basis mode is held to."""
+    out = {}
+    for name in ("rmat_s14_k50", "c1_er_n10000_k20", "band_n4096_k40"):
+        spec, k = CASES[name]
+        n, ro, ci = lz.generate_host(spec)
+        r64 = oracle.run_ref_final(ro, ci, k)
+        r32 = oracle.run_ref_final(ro, ci, k, single=True)
+        d = float(np.linalg.norm(r32["ans"] - r64["ans"]) / np.linalg.norm(r64["ans"]))
+        out[name + "__ans_f32"] = r32["ans"].astype(np.float32)
+        out[name + "__ref_f32_vs_f64"] = np.float64(d)
+        print(f"{name}: reference float vs double relative 2-norm {d:.3e}")
+    np.savez_compressed(os.path.join(HERE, "reference_float.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--float":
+        main_float()
+    else:
+        main()

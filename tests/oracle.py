@@ -142,7 +142,7 @@ def write_csr_bin(path, ro, ci):
         ci.tofile(f)
 
 
-def run_ref_final(ro, ci, k, x=None, cuda=False, iters=0, reps=1, want_output=True, csr_path=None):
+def run_ref_final(ro, ci, k, x=None, cuda=False, iters=0, reps=1, want_output=True, csr_path=None, single=False):
     """Runs the unmodified reference (parallel-final host path, or its CUDA path with cuda=True).
     -> dict(ans, alpha, beta, timings=[json per rep])"""
     with tempfile.TemporaryDirectory() as td:
@@ -156,6 +156,8 @@ def run_ref_final(ro, ci, k, x=None, cuda=False, iters=0, reps=1, want_output=Tr
             cmd += ["--x", xp]
         if cuda:
             cmd.append("--cuda")
+        if single:
+            cmd.append("--float")          # the reference's lanczosDecomp<float> instantiation
         if iters:
             cmd += ["--iters", str(iters)]
         out = os.path.join(td, "o")
