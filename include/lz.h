@@ -102,7 +102,8 @@ int lz_csr_upload(lz_ctx* ctx, uint64_t n, const uint32_t* row_offset, const uin
 /* Build the graph on the device (same bits as lz_graph_generate_host) and ingest it. */
 int lz_graph_generate(lz_ctx* ctx, const lz_graph_spec* spec);
 int lz_graph_info_get(lz_ctx* ctx, lz_graph_info* info_out);
-/* Full CSR in original order back to the host (buffers sized n+1 and nnz from lz_graph_info_get). Test / oracle hook. */
+/* Full CSR in original order back to the host (buffers sized n+1 and nnz from lz_graph_info_get). Test / oracle hook: a one-GPU
+ * context keeps that copy, a multi-GPU context drops it after sharding (9 GB per GPU at 2^27) unless LZ_KEEP_CSR=1 is set. */
 int lz_csr_download(lz_ctx* ctx, uint32_t* row_offset_out, uint32_t* col_idx_out);
 
 /* ---- hot path ---------------------------------------------------------------------------------------------------- */

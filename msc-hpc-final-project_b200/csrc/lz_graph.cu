@@ -50,14 +50,6 @@ __global__ void k_low32(const uint64_t* __restrict__ keys, uint64_t nnz, uint32_
   if (i < nnz) out[i] = (uint32_t)keys[i];
 }
 
-// sort key for the degree ordering: descending degree == ascending (~deg); value = original id
-__global__ void k_degree_keys(const uint32_t* __restrict__ ro, uint64_t n, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
-  uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n) return;
-  key[v] = ~(ro[v + 1] - ro[v]);
-  val[v] = (uint32_t)v;
-}
-
 __global__ void k_iota_u32(uint32_t* p, uint64_t n) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = (uint32_t)i;
@@ -95,17 +87,6 @@ __global__ void k_relabel(const uint32_t* __restrict__ sorted_old, uint64_t n, u
   uint32_t nw = (uint32_t)((l / cl) * (world * cl) + r * cl + (l % cl));
   old2new[old] = nw;
   new2old[nw] = old;
-}
-
-// local row l of rank r is sorted position l*world + r
-__global__ void k_local_lengths(const uint32_t* __restrict__ sorted_old, const uint32_t* __restrict__ ro, uint64_t n, uint32_t world,
-                                uint32_t rank, uint64_t n_loc, uint64_t block_rows, uint32_t* __restrict__ len) {
-  uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= n_loc) return;
-  uint64_t s = block_rows ? (uint64_t)rank * block_rows + l : l * world + rank;
-  uint32_t d = 0;
-  if (s < n) { uint32_t old = sorted_old[s]; d = ro[old + 1] - ro[old]; }
-  len[l] = d;
 }
 
 // one warp per local row: keys[row_ptr[l] + j] = (colblock << (32 + rowbits)) | (l << 32) | newcol, newcol = old2new[ci[ro[old] + j]]
@@ -249,7 +230,6 @@ __global__ void k_count_need(const uint32_t* __restrict__ bm_all, uint64_t words
   if ((threadIdx.x & 31) == 0 && acc) atomicAdd(counts + r, acc);
 }
 
-struct IsEmpty { __host__ __device__ uint64_t operator()(uint32_t k) const { return k == 0xFFFFFFFFu ? 1ull : 0ull; } };
 
 inline unsigned grid_for(uint64_t items, unsigned block) { return (unsigned)((items + block - 1) / block); }
 
@@ -304,43 +284,76 @@ static void make_plans(const uint32_t* bounds, uint32_t n_loc, uint32_t nblk, co
   }
 }
 
-// Takes ownership of ro_d / ci_d (original-order CSR on the device).
-int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, uint32_t* ci_d) {
-  lz_free_graph(c);
-  c->epoch++;   // any cached CUDA graph of the step loop refers to the old matrix
-  c->graph_id++;
-  c->orig_ro = ro_d; c->orig_ci = ci_d;
+// ---- ingest, in stages shared by the two sources of a graph ---------------------------------------------------------------
+//   (1) a full original-order CSR on this device (lz_csr_upload, lz_graph_generate on one GPU)
+//   (2) the counter-based generator, evaluated shard-wise on several GPUs (generate_sharded below): no rank ever holds more
+//       than its own rows
+// Both produce a degree array and then the keys (column block, local row, new column) of this rank's entries.
+struct Order {
+  DevBuf sorted_old, old2new;
+  bool natural = false;
+  uint64_t cl = 0, n_loc = 0, block_rows = 0, width = 0;
+  uint32_t nblk = 1;
+  int rowbits = 1;
+};
+
+__global__ void k_deg_from_ro(const uint32_t* __restrict__ ro, uint64_t n, uint32_t* __restrict__ deg) {
+  uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) deg[v] = ro[v + 1] - ro[v];
+}
+__global__ void k_degree_keys_deg(const uint32_t* __restrict__ deg, uint64_t n, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+  uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  key[v] = ~deg[v];
+  val[v] = (uint32_t)v;
+}
+__global__ void k_local_lengths_deg(const uint32_t* __restrict__ sorted_old, const uint32_t* __restrict__ deg, uint64_t n, uint32_t world,
+                                    uint32_t rank, uint64_t n_loc, uint64_t block_rows, uint32_t* __restrict__ len) {
+  uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_loc) return;
+  uint64_t s = block_rows ? (uint64_t)rank * block_rows + l : l * world + rank;
+  len[l] = s < n ? deg[sorted_old[s]] : 0u;
+}
+struct IsZero { __host__ __device__ uint64_t operator()(uint32_t d) const { return d == 0u ? 1ull : 0ull; } };
+struct AsU64 { __host__ __device__ uint64_t operator()(uint32_t d) const { return (uint64_t)d; } };
+
+// Stage 1-3: vertex order from the degrees, relabelling, local row pointer. `near` = stored entries within the locality radius
+// of the diagonal (global). Sets n, nnz, max_degree, empty_rows, natural_order, chunk_rows, ncolblk, n_loc, nnz_loc, new2old, row_ptr.
+static int make_order(lz_ctx* c, uint64_t n, uint64_t nnz, const uint32_t* deg_d, unsigned long long near, uint64_t radius, Order& o) {
   c->n = n; c->nnz = nnz;
   const uint32_t world = (uint32_t)c->world, rank = (uint32_t)c->rank;
   cudaStream_t st = c->stream;
-
   // 1. vertex order. Degree order (stable radix sort => ties keep ascending original id) by default; the natural order when
   //    the graph is band-like and not skewed (there the original numbering already has the locality that sorting would destroy).
-  DevBuf key_in, key_out, val_in, sorted_old, old2new, len, tmp, loc_d;
+  DevBuf key_in, key_out, val_in, len, tmp, cnt;
   LZ_CUDA(cudaMalloc(&key_in.p, n * 4)); LZ_CUDA(cudaMalloc(&key_out.p, n * 4));
-  LZ_CUDA(cudaMalloc(&val_in.p, n * 4)); LZ_CUDA(cudaMalloc(&sorted_old.p, n * 4));
-  LZ_CUDA(cudaMalloc(&loc_d.p, 8));
-  k_degree_keys<<<grid_for(n, 256), 256, 0, st>>>(ro_d, n, key_in.as<uint32_t>(), val_in.as<uint32_t>());
+  LZ_CUDA(cudaMalloc(&val_in.p, n * 4)); LZ_CUDA(cudaMalloc(&o.sorted_old.p, n * 4));
+  k_degree_keys_deg<<<grid_for(n, 256), 256, 0, st>>>(deg_d, n, key_in.as<uint32_t>(), val_in.as<uint32_t>());
   size_t tb = 0;
   LZ_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key_in.as<uint32_t>(), key_out.as<uint32_t>(), val_in.as<uint32_t>(),
-                                          sorted_old.as<uint32_t>(), (int64_t)n, 0, 32, st));
+                                          o.sorted_old.as<uint32_t>(), (int64_t)n, 0, 32, st));
   LZ_CUDA(cudaMalloc(&tmp.p, tb ? tb : 1));
   LZ_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key_in.as<uint32_t>(), key_out.as<uint32_t>(), val_in.as<uint32_t>(),
-                                          sorted_old.as<uint32_t>(), (int64_t)n, 0, 32, st));
+                                          o.sorted_old.as<uint32_t>(), (int64_t)n, 0, 32, st));
   uint32_t kfirst = 0;   // key = ~deg ascending: the first key belongs to the largest degree
-  unsigned long long near = 0;
-  const uint64_t radius = (n / 256 > 65536) ? n / 256 : 65536;
-  LZ_CUDA(cudaMemsetAsync(loc_d.p, 0, 8, st));
-  k_locality<<<(unsigned)c->sm_count * 8, 256, 0, st>>>(ro_d, ci_d, n, radius, (unsigned long long*)loc_d.p);
   LZ_CUDA(cudaMemcpyAsync(&kfirst, key_out.p, 4, cudaMemcpyDeviceToHost, st));
-  LZ_CUDA(cudaMemcpyAsync(&near, loc_d.p, 8, cudaMemcpyDeviceToHost, st));
-  LZ_CUDA(cudaStreamSynchronize(st));
+  {  // isolated vertices
+    size_t b5 = 0; DevBuf t5;
+    LZ_CUDA(cudaMalloc(&cnt.p, 8));
+    cub::TransformInputIterator<uint64_t, IsZero, const uint32_t*> it(deg_d, IsZero());
+    LZ_CUDA(cub::DeviceReduce::Sum(nullptr, b5, it, cnt.as<uint64_t>(), (int64_t)n, st));
+    LZ_CUDA(cudaMalloc(&t5.p, b5 ? b5 : 1));
+    LZ_CUDA(cub::DeviceReduce::Sum(t5.p, b5, it, cnt.as<uint64_t>(), (int64_t)n, st));
+    LZ_CUDA(cudaMemcpyAsync(&c->empty_rows, cnt.p, 8, cudaMemcpyDeviceToHost, st));
+    LZ_CUDA(cudaStreamSynchronize(st));
+  }
   c->max_degree = ~kfirst;
   const double avg_deg = (double)nnz / (double)n;
   bool natural = radius < n / 8 && c->max_degree <= LZ_SELL_LONG && (double)c->max_degree <= 8.0 * (avg_deg > 1.0 ? avg_deg : 1.0) &&
                  (double)near >= 0.5 * (double)nnz;
   if (const char* e = getenv("LZ_ORDER")) natural = (e[0] == 'n');
   c->natural_order = natural;
+  o.natural = natural;
 
   // Rows per rank and column blocks. A column block (= chunk) is `cl` rows of every rank: a window of world * cl
   // entries of the gathered vector that one SpMV pass gathers from; it is sized to stay L2-resident (64 MiB measured
@@ -362,34 +375,31 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
   c->chunk_rows = cl;
   if (n_pad > 0xFFFFFFFEull) return lz_fail(LZ_ERR_ARG, "n = %llu too large for 32-bit vertex ids", (unsigned long long)n);
   c->n_loc = n_loc;
-  LZ_CUDA(cudaMalloc(&old2new.p, n * 4)); LZ_CUDA(cudaMalloc(&len.p, (n_loc + 1) * 4));
+  c->ncolblk = nblk;
+  o.cl = cl; o.n_loc = n_loc; o.block_rows = block_rows; o.nblk = nblk; o.rowbits = bits_for(n_loc); o.width = (uint64_t)world * cl;
+  LZ_CUDA(cudaMalloc(&o.old2new.p, n * 4)); LZ_CUDA(cudaMalloc(&len.p, (n_loc + 1) * 4));
   LZ_CUDA(cudaMalloc((void**)&c->new2old, n_pad * 4));
   LZ_CUDA(cudaMalloc((void**)&c->row_ptr, (n_loc + 1) * 4));
-  if (natural) k_iota_u32<<<grid_for(n, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), n);
+  if (natural) k_iota_u32<<<grid_for(n, 256), 256, 0, st>>>(o.sorted_old.as<uint32_t>(), n);
 
   // 2. relabel
   k_fill_u32<<<grid_for(n_pad, 256), 256, 0, st>>>(c->new2old, n_pad, 0xFFFFFFFFu);
-  k_relabel<<<grid_for(n, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), n, world, cl, block_rows, old2new.as<uint32_t>(), c->new2old);
+  k_relabel<<<grid_for(n, 256), 256, 0, st>>>(o.sorted_old.as<uint32_t>(), n, world, cl, block_rows, o.old2new.as<uint32_t>(), c->new2old);
 
-  // 3. local row pointer
-  k_local_lengths<<<grid_for(n_loc, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), ro_d, n, world, rank, n_loc, block_rows, len.as<uint32_t>());
+  // 3. local row pointer (total row lengths)
+  k_local_lengths_deg<<<grid_for(n_loc, 256), 256, 0, st>>>(o.sorted_old.as<uint32_t>(), deg_d, n, world, rank, n_loc, block_rows, len.as<uint32_t>());
   LZ_CUDA(cudaMemsetAsync(len.as<uint32_t>() + n_loc, 0, 4, st));
   {
     DevBuf t2; size_t b2 = 0;
     LZ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b2, len.as<uint32_t>(), c->row_ptr, (int64_t)(n_loc + 1), st));
     LZ_CUDA(cudaMalloc(&t2.p, b2 ? b2 : 1));
     LZ_CUDA(cub::DeviceScan::ExclusiveSum(t2.p, b2, len.as<uint32_t>(), c->row_ptr, (int64_t)(n_loc + 1), st));
-    LZ_CUDA(cudaStreamSynchronize(st));
   }
-  // number of isolated vertices: rows with ~deg == 0xFFFFFFFF are at the end of key_out -> count via binary search on host-side copy is
-  // overkill; use the original row offsets instead (empty rows = n - #rows with ro[v+1] > ro[v]); computed with a device reduction below.
-  uint32_t nnz_loc32 = 0;
-  LZ_CUDA(cudaMemcpy(&nnz_loc32, c->row_ptr + n_loc, 4, cudaMemcpyDeviceToHost));
   {
     // the scan is 32-bit: guard against wrap-around by summing lengths in 64 bit
     DevBuf t3, s64; size_t b3 = 0;
     LZ_CUDA(cudaMalloc(&s64.p, 8));
-    cub::TransformInputIterator<uint64_t, cub::CastOp<uint64_t>, const uint32_t*> it(len.as<uint32_t>(), cub::CastOp<uint64_t>());
+    cub::TransformInputIterator<uint64_t, AsU64, const uint32_t*> it(len.as<uint32_t>(), AsU64());
     LZ_CUDA(cub::DeviceReduce::Sum(nullptr, b3, it, s64.as<uint64_t>(), (int64_t)n_loc, st));
     LZ_CUDA(cudaMalloc(&t3.p, b3 ? b3 : 1));
     LZ_CUDA(cub::DeviceReduce::Sum(t3.p, b3, it, s64.as<uint64_t>(), (int64_t)n_loc, st));
@@ -399,30 +409,49 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
     if (total > 0xFFFFFFFFull) return lz_fail(LZ_ERR_ARG, "local nnz %llu does not fit 32-bit row offsets", (unsigned long long)total);
     c->nnz_loc = total;
   }
+  return LZ_OK;
+}
 
-  // 4. column blocks were fixed above (nblk windows of world * cl entries)
-  const int rowbits = bits_for(n_loc);
-  const uint64_t width = (uint64_t)world * cl;
-  c->ncolblk = nblk;
-
-  // 5. local column lists in the new numbering: column-block-major, row-major, ascending column (one 64-bit radix sort)
+// Stage 5-7: sort this rank's keys (column-block-major, row-major, ascending column), optionally dropping duplicates (generator
+// candidates), then the per-block row pointers, the CSR launch plans and the sliced layout.
+static int finish_local(lz_ctx* c, const Order& o, DevBuf& k_in, uint64_t nkeys, bool dedupe) {
+  cudaStream_t st = c->stream;
+  const uint64_t n_loc = o.n_loc;
+  const uint32_t nblk = o.nblk;
+  const int rowbits = o.rowbits;
+  const bool natural = o.natural;
   {
-    DevBuf k_in, k_out, t4; size_t b4 = 0;
-    uint64_t m = c->nnz_loc;
-    LZ_CUDA(cudaMalloc(&k_in.p, (m ? m : 1) * 8)); LZ_CUDA(cudaMalloc(&k_out.p, (m ? m : 1) * 8));
+    DevBuf k_out, t4; size_t b4 = 0;
+    const uint64_t m = c->nnz_loc;
+    LZ_CUDA(cudaMalloc(&k_out.p, (nkeys ? nkeys : 1) * 8));
     LZ_CUDA(cudaMalloc((void**)&c->col, (m ? m : 1) * 4));
     LZ_CUDA(cudaMalloc((void**)&c->seg_store, (uint64_t)nblk * (n_loc + 1) * 4));
-    if (m) {
-      k_local_keys<<<grid_for(n_loc * 32, 256), 256, 0, st>>>(sorted_old.as<uint32_t>(), ro_d, ci_d, old2new.as<uint32_t>(), c->row_ptr, n,
-                                                                world, rank, n_loc, block_rows, width, rowbits, k_in.as<uint64_t>());
+    const uint64_t* sorted = k_out.as<uint64_t>();
+    if (nkeys) {
       int end_bit = 32 + rowbits + (nblk > 1 ? bits_for(nblk) : 0);
       if (end_bit > 64) end_bit = 64;
-      LZ_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, b4, k_in.as<uint64_t>(), k_out.as<uint64_t>(), (int64_t)m, 0, end_bit, st));
+      LZ_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, b4, k_in.as<uint64_t>(), k_out.as<uint64_t>(), (int64_t)nkeys, 0, end_bit, st));
       LZ_CUDA(cudaMalloc(&t4.p, b4 ? b4 : 1));
-      LZ_CUDA(cub::DeviceRadixSort::SortKeys(t4.p, b4, k_in.as<uint64_t>(), k_out.as<uint64_t>(), (int64_t)m, 0, end_bit, st));
-      k_low32<<<grid_for(m, 256), 256, 0, st>>>(k_out.as<uint64_t>(), m, c->col);
+      LZ_CUDA(cub::DeviceRadixSort::SortKeys(t4.p, b4, k_in.as<uint64_t>(), k_out.as<uint64_t>(), (int64_t)nkeys, 0, end_bit, st));
+      if (dedupe) {
+        DevBuf nsel, tu; size_t ub = 0;
+        LZ_CUDA(cudaMalloc(&nsel.p, 8));
+        LZ_CUDA(cub::DeviceSelect::Unique(nullptr, ub, k_out.as<uint64_t>(), k_in.as<uint64_t>(), nsel.as<int64_t>(), (int64_t)nkeys, st));
+        LZ_CUDA(cudaMalloc(&tu.p, ub ? ub : 1));
+        LZ_CUDA(cub::DeviceSelect::Unique(tu.p, ub, k_out.as<uint64_t>(), k_in.as<uint64_t>(), nsel.as<int64_t>(), (int64_t)nkeys, st));
+        int64_t nu = 0;
+        LZ_CUDA(cudaMemcpyAsync(&nu, nsel.p, 8, cudaMemcpyDeviceToHost, st));
+        LZ_CUDA(cudaStreamSynchronize(st));
+        if ((uint64_t)nu != m)
+          return lz_fail(LZ_ERR_ARG, "sharded graph construction is inconsistent: %lld distinct local entries, degrees say %llu", (long long)nu,
+                         (unsigned long long)m);
+        sorted = k_in.as<uint64_t>();
+      } else if (nkeys != m) {
+        return lz_fail(LZ_ERR_ARG, "local key count %llu != local nnz %llu", (unsigned long long)nkeys, (unsigned long long)m);
+      }
+      if (m) k_low32<<<grid_for(m, 256), 256, 0, st>>>(sorted, m, c->col);
     }
-    k_block_row_ptr<<<grid_for((uint64_t)nblk * (n_loc + 1), 256), 256, 0, st>>>(k_out.as<uint64_t>(), m, n_loc, nblk, rowbits, c->seg_store);
+    k_block_row_ptr<<<grid_for((uint64_t)nblk * (n_loc + 1), 256), 256, 0, st>>>(sorted, m, n_loc, nblk, rowbits, c->seg_store);
     LZ_CUDA(cudaStreamSynchronize(st));
     for (uint32_t b = 0; b < nblk; b++) c->seg[b] = c->seg_store + (uint64_t)b * (n_loc + 1);
     c->seg[nblk] = nullptr;
@@ -459,18 +488,6 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
       const uint32_t rows_per_item = (LZ_SPMV_BLOCK >> 5) * LZ_SPMV_ROWS_PER_GROUP;
       c->plan_warp.nitems = (uint32_t)((n_loc + rows_per_item - 1) / rows_per_item);
     }
-    // isolated vertices: local rows with length 0 start at out_h[5]; every rank sees ~1/world of them. Global count from the
-    // sorted degree keys: positions s with deg == 0 are the tail; first such s = lower_bound over all ranks -> computed on rank-agnostic data:
-    // empty_global = n - (#vertices with deg > 0). Use the degree keys (ascending ~deg): deg == 0 <=> key == 0xFFFFFFFF.
-    DevBuf cnt; size_t b5 = 0; DevBuf t5;
-    LZ_CUDA(cudaMalloc(&cnt.p, 8));
-    // count keys equal to 0xFFFFFFFF via a transform-reduce
-    cub::TransformInputIterator<uint64_t, IsEmpty, const uint32_t*> it(key_out.as<uint32_t>(), IsEmpty());
-    LZ_CUDA(cub::DeviceReduce::Sum(nullptr, b5, it, cnt.as<uint64_t>(), (int64_t)n, st));
-    LZ_CUDA(cudaMalloc(&t5.p, b5 ? b5 : 1));
-    LZ_CUDA(cub::DeviceReduce::Sum(t5.p, b5, it, cnt.as<uint64_t>(), (int64_t)n, st));
-    LZ_CUDA(cudaMemcpyAsync(&c->empty_rows, cnt.p, 8, cudaMemcpyDeviceToHost, st));
-    LZ_CUDA(cudaStreamSynchronize(st));
   }
   // 7. sliced layout for the default SpMV
   {
@@ -529,6 +546,200 @@ int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, ui
   return LZ_OK;
 }
 
+// Takes ownership of ro_d / ci_d (original-order CSR on the device).
+int lz_ingest_device_csr(lz_ctx* c, uint64_t n, uint64_t nnz, uint32_t* ro_d, uint32_t* ci_d) {
+  lz_free_graph(c);
+  c->epoch++;   // any cached CUDA graph of the step loop refers to the old matrix
+  c->graph_id++;
+  c->orig_ro = ro_d; c->orig_ci = ci_d;
+  const uint32_t world = (uint32_t)c->world, rank = (uint32_t)c->rank;
+  cudaStream_t st = c->stream;
+  DevBuf deg, loc_d;
+  LZ_CUDA(cudaMalloc(&deg.p, n * 4)); LZ_CUDA(cudaMalloc(&loc_d.p, 8));
+  k_deg_from_ro<<<grid_for(n, 256), 256, 0, st>>>(ro_d, n, deg.as<uint32_t>());
+  unsigned long long near = 0;
+  const uint64_t radius = (n / 256 > 65536) ? n / 256 : 65536;
+  LZ_CUDA(cudaMemsetAsync(loc_d.p, 0, 8, st));
+  k_locality<<<(unsigned)c->sm_count * 8, 256, 0, st>>>(ro_d, ci_d, n, radius, (unsigned long long*)loc_d.p);
+  LZ_CUDA(cudaMemcpyAsync(&near, loc_d.p, 8, cudaMemcpyDeviceToHost, st));
+  LZ_CUDA(cudaStreamSynchronize(st));
+  Order o;
+  LZ_TRY(make_order(c, n, nnz, deg.as<uint32_t>(), near, radius, o));
+  // 5. local column lists in the new numbering: one key per stored entry of this rank's rows
+  DevBuf k_in;
+  const uint64_t m = c->nnz_loc;
+  LZ_CUDA(cudaMalloc(&k_in.p, (m ? m : 1) * 8));
+  if (m)
+    k_local_keys<<<grid_for(o.n_loc * 32, 256), 256, 0, st>>>(o.sorted_old.as<uint32_t>(), ro_d, ci_d, o.old2new.as<uint32_t>(), c->row_ptr, n,
+                                                               world, rank, o.n_loc, o.block_rows, o.width, o.rowbits, k_in.as<uint64_t>());
+  LZ_TRY(finish_local(c, o, k_in, m, false));
+  // The original-order CSR only serves lz_csr_download (a test / oracle hook). On several GPUs it is dead weight on every rank
+  // (C4: 9.1 GB per GPU): dropped unless LZ_KEEP_CSR=1 asks for it. One GPU keeps it (LZ_KEEP_CSR=0 drops it there too).
+  bool keep = c->world == 1;
+  if (const char* e = getenv("LZ_KEEP_CSR")) keep = atoi(e) != 0;
+  if (!keep) {
+    cudaFree(c->orig_ro); cudaFree(c->orig_ci);
+    c->orig_ro = c->orig_ci = nullptr;
+  }
+  return LZ_OK;
+}
+
+// ---- sharded construction of a generated graph (several GPUs) ---------------------------------------------------------------
+// The generators are pure functions of the candidate index, so no rank needs the whole graph:
+//   A. every rank scans all candidates and keeps the oriented entries whose ORIGINAL row lies in its slice of [0, n): sort +
+//      unique gives the degrees of that slice; the slices are all-gathered (4 n bytes), as is the locality count.
+//   B. every rank derives the same vertex order and relabelling from the degree array (make_order).
+//   C. every rank scans the candidates again and keeps the oriented entries whose row it OWNS in the new numbering, directly as
+//      (column block, local row, new column) keys; sort + unique must leave exactly the number of entries the degrees promise.
+// Work and memory per rank are O(nnz / world + n) (plus two cheap scans of the candidate space); the reference builds the
+// whole matrix in a std::set on one host thread (adjMatrix.cc:21-46).
+struct SelRange {      // phase A: original row in [lo, hi)
+  uint32_t lo, hi;
+  __device__ bool operator()(uint32_t r, uint32_t cidx, uint64_t* key) const {
+    if (r < lo || r >= hi) return false;
+    *key = ((uint64_t)r << 32) | cidx;
+    return true;
+  }
+};
+struct SelOwner {      // phase C: row owned by this rank in the new numbering (chunk-major ids, see k_relabel)
+  const uint32_t* old2new;
+  uint64_t cl, width;
+  uint32_t world, rank;
+  int rowbits;
+  __device__ bool operator()(uint32_t r, uint32_t cidx, uint64_t* key) const {
+    const uint64_t nr = old2new[r];
+    const uint64_t ch = nr / width, rem = nr - ch * width;
+    if (rem / cl != rank) return false;
+    const uint64_t l = ch * cl + (rem - (uint64_t)rank * cl);
+    const uint64_t nc = old2new[cidx];
+    *key = ((nc / width) << (32 + rowbits)) | (l << 32) | nc;
+    return true;
+  }
+};
+template <class Sel>
+__global__ void __launch_bounds__(256) k_gen_select(lz_gen_params p, Sel sel, uint64_t* __restrict__ out, unsigned long long* __restrict__ cursor) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t total = (p.m + 1 + 31) & ~31ull;      // whole warps stay converged for the ballots
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t u = 0, v = 0;
+    if (e <= p.m) lz_gen_edge(p, e, &u, &v);
+    const bool edge = e <= p.m && u != v;
+#pragma unroll
+    for (int orient = 0; orient < 2; orient++) {
+      uint64_t key = 0;
+      const bool take = edge && sel(orient ? v : u, orient ? u : v, &key);
+      const unsigned mask = __ballot_sync(0xffffffffu, take);
+      if (!mask) continue;
+      const int leader = __ffs(mask) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(mask));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (take && out) out[base + __popc(mask & ((1u << lane) - 1u))] = key;
+    }
+  }
+}
+// deg[i] = number of (sorted, unique) keys with row lo + i, i < rows
+__global__ void k_range_degrees(const uint64_t* __restrict__ keys, uint64_t nkeys, uint32_t lo, uint32_t rows, uint32_t n, uint32_t* __restrict__ deg) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const uint64_t r = (uint64_t)lo + i;
+  if (r >= n) { deg[i] = 0u; return; }
+  auto lower = [&](uint64_t target) {
+    uint64_t a = 0, b = nkeys;
+    while (a < b) { const uint64_t mid = (a + b) >> 1; if (keys[mid] < target) a = mid + 1; else b = mid; }
+    return a;
+  };
+  deg[i] = (uint32_t)(lower((r + 1) << 32) - lower(r << 32));
+}
+__global__ void k_locality_keys(const uint64_t* __restrict__ keys, uint64_t nkeys, uint64_t radius, unsigned long long* __restrict__ out) {
+  unsigned long long acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nkeys; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = keys[i] >> 32, cc = keys[i] & 0xFFFFFFFFull;
+    acc += (cc > r ? cc - r : r - cc) <= radius;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+template <class Sel>
+static int gen_select(lz_ctx* c, const lz_gen_params& p, const Sel& sel, DevBuf& keys, uint64_t* nkeys_out) {
+  cudaStream_t st = c->stream;
+  DevBuf cur;
+  LZ_CUDA(cudaMalloc(&cur.p, 8));
+  const unsigned grid = (unsigned)c->sm_count * 16;
+  unsigned long long cnt = 0;
+  LZ_CUDA(cudaMemsetAsync(cur.p, 0, 8, st));
+  k_gen_select<Sel><<<grid, 256, 0, st>>>(p, sel, nullptr, (unsigned long long*)cur.p);          // count
+  LZ_CUDA(cudaMemcpyAsync(&cnt, cur.p, 8, cudaMemcpyDeviceToHost, st));
+  LZ_CUDA(cudaStreamSynchronize(st));
+  if (cudaMalloc(&keys.p, (cnt ? cnt : 1) * 8) != cudaSuccess) { cudaGetLastError(); return lz_fail(LZ_ERR_ALLOC, "cannot allocate %llu shard keys", cnt); }
+  LZ_CUDA(cudaMemsetAsync(cur.p, 0, 8, st));
+  k_gen_select<Sel><<<grid, 256, 0, st>>>(p, sel, keys.as<uint64_t>(), (unsigned long long*)cur.p);   // emit (order irrelevant: sorted next)
+  LZ_CUDA(cudaStreamSynchronize(st));
+  *nkeys_out = cnt;
+  return LZ_OK;
+}
+
+static int generate_sharded(lz_ctx* c, const lz_gen_params& p) {
+  lz_free_graph(c);
+  c->epoch++;
+  c->graph_id++;
+  cudaStream_t st = c->stream;
+  const uint32_t world = (uint32_t)c->world, rank = (uint32_t)c->rank;
+  const uint64_t n = p.n;
+  const uint64_t rows_per = (n + world - 1) / world;
+  const uint64_t lo = (uint64_t)rank * rows_per, hi = lo + rows_per < n ? lo + rows_per : n;
+  DevBuf deg_all, near_d;
+  LZ_CUDA(cudaMalloc(&deg_all.p, rows_per * world * 4));
+  LZ_CUDA(cudaMalloc(&near_d.p, 16));
+  LZ_CUDA(cudaMemsetAsync(near_d.p, 0, 16, st));
+  const uint64_t radius = (n / 256 > 65536) ? n / 256 : 65536;
+  {  // A. degrees of my slice of the original numbering
+    DevBuf ka, kb, tmp, nsel;
+    uint64_t na = 0;
+    LZ_TRY(gen_select(c, p, SelRange{(uint32_t)(lo < n ? lo : n), (uint32_t)hi}, ka, &na));
+    LZ_CUDA(cudaMalloc(&kb.p, (na ? na : 1) * 8)); LZ_CUDA(cudaMalloc(&nsel.p, 8));
+    int64_t nu = 0;
+    if (na) {
+      size_t tb = 0, ub = 0;
+      LZ_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, ka.as<uint64_t>(), kb.as<uint64_t>(), (int64_t)na, 0, 64, st));
+      LZ_CUDA(cub::DeviceSelect::Unique(nullptr, ub, kb.as<uint64_t>(), ka.as<uint64_t>(), nsel.as<int64_t>(), (int64_t)na, st));
+      LZ_CUDA(cudaMalloc(&tmp.p, (tb > ub ? tb : ub) + 1));
+      LZ_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, ka.as<uint64_t>(), kb.as<uint64_t>(), (int64_t)na, 0, 64, st));
+      LZ_CUDA(cub::DeviceSelect::Unique(tmp.p, ub, kb.as<uint64_t>(), ka.as<uint64_t>(), nsel.as<int64_t>(), (int64_t)na, st));
+      LZ_CUDA(cudaMemcpyAsync(&nu, nsel.p, 8, cudaMemcpyDeviceToHost, st));
+      LZ_CUDA(cudaStreamSynchronize(st));
+    }
+    uint32_t* mine = deg_all.as<uint32_t>() + (uint64_t)rank * rows_per;
+    k_range_degrees<<<grid_for(rows_per, 256), 256, 0, st>>>(ka.as<uint64_t>(), (uint64_t)nu, (uint32_t)lo, (uint32_t)rows_per, (uint32_t)n, mine);
+    if (nu) k_locality_keys<<<(unsigned)c->sm_count * 8, 256, 0, st>>>(ka.as<uint64_t>(), (uint64_t)nu, radius, (unsigned long long*)near_d.p);
+    LZ_NCCL(lz_nccl()->AllGather(mine, deg_all.p, rows_per, ncclUint32, c->comm, st));
+    LZ_NCCL(lz_nccl()->AllReduce(near_d.p, near_d.p, 1, ncclUint64, ncclSum, c->comm, st));
+    LZ_CUDA(cudaStreamSynchronize(st));
+  }
+  unsigned long long near = 0;
+  LZ_CUDA(cudaMemcpy(&near, near_d.p, 8, cudaMemcpyDeviceToHost));
+  uint64_t nnz = 0;
+  {
+    DevBuf s64, t3; size_t b3 = 0;
+    LZ_CUDA(cudaMalloc(&s64.p, 8));
+    cub::TransformInputIterator<uint64_t, AsU64, const uint32_t*> it(deg_all.as<uint32_t>(), AsU64());
+    LZ_CUDA(cub::DeviceReduce::Sum(nullptr, b3, it, s64.as<uint64_t>(), (int64_t)n, st));
+    LZ_CUDA(cudaMalloc(&t3.p, b3 ? b3 : 1));
+    LZ_CUDA(cub::DeviceReduce::Sum(t3.p, b3, it, s64.as<uint64_t>(), (int64_t)n, st));
+    LZ_CUDA(cudaMemcpyAsync(&nnz, s64.p, 8, cudaMemcpyDeviceToHost, st));
+    LZ_CUDA(cudaStreamSynchronize(st));
+  }
+  // B. the same order on every rank
+  Order o;
+  LZ_TRY(make_order(c, n, nnz, deg_all.as<uint32_t>(), near, radius, o));
+  cudaFree(deg_all.release());
+  // C. my rows, straight in the final key form
+  DevBuf kc;
+  uint64_t nc = 0;
+  LZ_TRY(gen_select(c, p, SelOwner{o.old2new.as<uint32_t>(), o.cl, o.width, world, rank, o.rowbits}, kc, &nc));
+  return finish_local(c, o, kc, nc, true);
+}
 
 // Needed-columns exchange, set up once per graph/vector allocation; collective over the NCCL communicator.
 // Every rank marks the columns its rows reference, the bitmaps are all-gathered, and each rank derives, per peer, the
@@ -616,6 +827,13 @@ extern "C" int lz_graph_generate(lz_ctx* c, const lz_graph_spec* spec) {
   lz_gen_params p;
   if (lz_gen_prepare(spec, &p)) return lz_fail(LZ_ERR_ARG, "bad graph spec (kind %u)", spec->kind);
   cudaStream_t st = c->stream;
+  bool sharded = c->world > 1;
+  if (const char* e = getenv("LZ_KEEP_CSR")) if (atoi(e) != 0) sharded = false;      // the full CSR is wanted back (lz_csr_download)
+  if (const char* e = getenv("LZ_SHARDED_INGEST")) sharded = c->world > 1 && atoi(e) != 0;
+  if (sharded) {
+    c->have_x = c->have_tridiag = c->have_coef = c->have_ans = false;
+    return generate_sharded(c, p);
+  }
   const uint64_t nkeys = 2 * (p.m + 1);
   DevBuf k_in, k_out, tmp, nsel;
   LZ_CUDA(cudaMalloc(&k_in.p, nkeys * 8)); LZ_CUDA(cudaMalloc(&k_out.p, nkeys * 8)); LZ_CUDA(cudaMalloc(&nsel.p, 8));
@@ -661,7 +879,8 @@ extern "C" int lz_graph_info_get(lz_ctx* c, lz_graph_info* out) {
 
 extern "C" int lz_csr_download(lz_ctx* c, uint32_t* row_offset_out, uint32_t* col_idx_out) {
   if (!c || !row_offset_out || !col_idx_out) return lz_fail(LZ_ERR_ARG, "null argument");
-  if (!c->orig_ro) return lz_fail(LZ_ERR_ARG, "no graph loaded");
+  if (!c->row_ptr) return lz_fail(LZ_ERR_ARG, "no graph loaded");
+  if (!c->orig_ro) return lz_fail(LZ_ERR_ARG, "the original-order CSR was not kept (multi-GPU contexts drop it; set LZ_KEEP_CSR=1 before loading the graph)");
   LZ_CUDA(cudaSetDevice(c->device));
   LZ_CUDA(cudaMemcpyAsync(row_offset_out, c->orig_ro, (c->n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
   LZ_CUDA(cudaMemcpyAsync(col_idx_out, c->orig_ci, c->nnz * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -122,14 +122,17 @@ __device__ __forceinline__ double red_consume(const lz_red& red, int kind, doubl
   return red_consume_seq(red, kind, red.seq, sm_bcast);
 }
 
-// Basis storage: fp64, or fp32 (LZ_BASIS_F32: half the bytes of every pass over V; all arithmetic stays fp64).
-template <class TV> __device__ __forceinline__ double2 ld_pair(const TV* base, uint64_t i2);
-template <> __device__ __forceinline__ double2 ld_pair<double>(const double* base, uint64_t i2) {
-  return __ldcs(reinterpret_cast<const double2*>(base) + i2);
+// Basis storage: fp64, or fp32 (LZ_BASIS_F32: half the bytes of every pass over V; all arithmetic stays fp64). Every thread
+// moves 16 bytes per load either way: a group of kEpt<TV> consecutive entries (2 doubles or 4 floats).
+template <class TV> struct ept { static constexpr int value = 16 / sizeof(TV); };
+template <class TV> __device__ __forceinline__ void ld_group(const TV* base, uint64_t g, double (&v)[ept<TV>::value]);
+template <> __device__ __forceinline__ void ld_group<double>(const double* base, uint64_t g, double (&v)[2]) {
+  const double2 d = __ldcs(reinterpret_cast<const double2*>(base) + g);
+  v[0] = d.x; v[1] = d.y;
 }
-template <> __device__ __forceinline__ double2 ld_pair<float>(const float* base, uint64_t i2) {
-  const float2 f = __ldcs(reinterpret_cast<const float2*>(base) + i2);
-  return make_double2((double)f.x, (double)f.y);
+template <> __device__ __forceinline__ void ld_group<float>(const float* base, uint64_t g, double (&v)[4]) {
+  const float4 f = __ldcs(reinterpret_cast<const float4*>(base) + g);
+  v[0] = (double)f.x; v[1] = (double)f.y; v[2] = (double)f.z; v[3] = (double)f.w;
 }
 
 // Deterministic grid reduction tail. Thread 0 of every CTA passes its CTA value; the last CTA to arrive sums all
@@ -1014,42 +1017,53 @@ template <class TV>
 __global__ void __launch_bounds__(kBlock) k_multidot(const TV* __restrict__ V, uint64_t ldv, uint32_t nvec, const double* __restrict__ w,
                                                      uint64_t n, double* partials /* [nvec][grid] */, unsigned int* ticket, double* h_out,
                                                      const int* __restrict__ skip) {
+  constexpr int E = ept<TV>::value;
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
   if (skip && *skip) return;   // second Gram-Schmidt pass not needed (decided on the device, see k_reorth_decide)
-  const uint64_t n2 = n >> 1;
-  const double2* w2 = reinterpret_cast<const double2*>(w);
-  for (uint32_t t0 = 0; t0 < nvec; t0 += kDotTile) {
-    double acc[kDotTile];
+  const uint64_t ng = n / E, ldg = ldv / E;         // whole 16-byte groups; the tail (n % E entries) is handled by thread 0 below
+  // w is re-read once per tile of T vectors. fp32 basis: a vector costs half the bytes, so the tile is twice as tall (16) to
+  // keep the re-read at 1/8 of the traffic; it is loaded in two batches of 8 x 16 bytes per thread.
+  constexpr int T = (E == 4) ? 2 * kDotTile : kDotTile;
+  for (uint32_t t0 = 0; t0 < nvec; t0 += T) {
+    double acc[T];
 #pragma unroll
-    for (int u = 0; u < kDotTile; u++) acc[u] = 0.0;
-    const uint32_t nt = min((uint32_t)kDotTile, nvec - t0);
+    for (int u = 0; u < T; u++) acc[u] = 0.0;
+    const uint32_t nt = min((uint32_t)T, nvec - t0);
     const TV* vb = V + (uint64_t)t0 * ldv;
-    const uint64_t ld2 = ldv >> 1;
-    if (nt == kDotTile) {
-      for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
-        const double2 wv = w2[i];
-        double2 vv[kDotTile];
+    for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < ng; i += (uint64_t)gridDim.x * kBlock) {
+      double wv[E];
+      ld_group<double>(w, i * (E / 2), *reinterpret_cast<double(*)[2]>(&wv[0]));
+      if constexpr (E == 4) ld_group<double>(w, i * 2 + 1, *reinterpret_cast<double(*)[2]>(&wv[2]));
 #pragma unroll
-        for (int u = 0; u < kDotTile; u++) vv[u] = ld_pair<TV>(vb, (uint64_t)u * ld2 + i);
+      for (int sub = 0; sub < T / kDotTile; sub++) {
+        if ((uint32_t)(sub * kDotTile) >= nt) break;
+        double vv[kDotTile][E];
+        if (nt >= (uint32_t)((sub + 1) * kDotTile)) {
 #pragma unroll
-        for (int u = 0; u < kDotTile; u++) { acc[u] += vv[u].x * wv.x; acc[u] += vv[u].y * wv.y; }
-      }
-    } else {
-      for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
-        const double2 wv = w2[i];
+          for (int u = 0; u < kDotTile; u++) ld_group<TV>(vb, (uint64_t)(sub * kDotTile + u) * ldg + i, vv[u]);
 #pragma unroll
-        for (int u = 0; u < kDotTile; u++)
-          if (u < (int)nt) { const double2 vv = ld_pair<TV>(vb, (uint64_t)u * ld2 + i); acc[u] += vv.x * wv.x; acc[u] += vv.y * wv.y; }
+          for (int u = 0; u < kDotTile; u++)
+#pragma unroll
+            for (int e = 0; e < E; e++) acc[sub * kDotTile + u] += vv[u][e] * wv[e];
+        } else {
+#pragma unroll
+          for (int u = 0; u < kDotTile; u++)
+            if ((uint32_t)(sub * kDotTile + u) < nt) {
+              ld_group<TV>(vb, (uint64_t)(sub * kDotTile + u) * ldg + i, vv[u]);
+#pragma unroll
+              for (int e = 0; e < E; e++) acc[sub * kDotTile + u] += vv[u][e] * wv[e];
+            }
+        }
       }
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      for (uint64_t r = ng * E; r < n; r++)
 #pragma unroll
-      for (int u = 0; u < kDotTile; u++)
-        if (u < (int)nt) acc[u] += (double)V[(uint64_t)(t0 + u) * ldv + n - 1] * w[n - 1];
-    }
+        for (int u = 0; u < T; u++)
+          if (u < (int)nt) acc[u] += (double)V[(uint64_t)(t0 + u) * ldv + r] * w[r];
 #pragma unroll
-    for (int u = 0; u < kDotTile; u++) {
+    for (int u = 0; u < T; u++) {
       if (u < (int)nt) {
         double s = block_sum(acc[u], sm);
         if (threadIdx.x == 0) partials[(uint64_t)(t0 + u) * gridDim.x + blockIdx.x] = s;
@@ -1083,41 +1097,52 @@ template <class TV>
 __global__ void __launch_bounds__(kBlock) k_combine(const TV* __restrict__ V, uint64_t ldv, uint32_t nvec, const double* __restrict__ coef,
                                                     double sign, const double* base, double* out, uint64_t n, double* partials,
                                                     unsigned int* ticket, double* norm2_out, const int* __restrict__ skip) {
+  constexpr int E = ept<TV>::value;
   extern __shared__ double s_coef[];
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
   if (skip && *skip) return;
   for (uint32_t t = threadIdx.x; t < nvec; t += kBlock) s_coef[t] = sign * coef[t];
   __syncthreads();
-  const uint64_t n2 = n >> 1, ld2 = ldv >> 1;
+  const uint64_t ng = n / E, ldg = ldv / E;
   const double2* b2 = reinterpret_cast<const double2*>(base);
   double2* o2 = reinterpret_cast<double2*>(out);
   double nacc = 0.0;
-  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * kBlock) {
-    double2 acc = base ? b2[i] : make_double2(0.0, 0.0);
+  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < ng; i += (uint64_t)gridDim.x * kBlock) {
+    double acc[E];
+#pragma unroll
+    for (int h = 0; h < E / 2; h++) {
+      const double2 bv = base ? b2[i * (E / 2) + h] : make_double2(0.0, 0.0);
+      acc[2 * h] = bv.x; acc[2 * h + 1] = bv.y;
+    }
     uint32_t t = 0;
     for (; t + 8 <= nvec; t += 8) {
-      double2 vv[8];
+      double vv[8][E];
 #pragma unroll
-      for (int u = 0; u < 8; u++) vv[u] = ld_pair<TV>(V, (uint64_t)(t + u) * ld2 + i);
+      for (int u = 0; u < 8; u++) ld_group<TV>(V, (uint64_t)(t + u) * ldg + i, vv[u]);
 #pragma unroll
-      for (int u = 0; u < 8; u++) { acc.x += s_coef[t + u] * vv[u].x; acc.y += s_coef[t + u] * vv[u].y; }
+      for (int u = 0; u < 8; u++)
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[e] += s_coef[t + u] * vv[u][e];
     }
     for (; t < nvec; t++) {
-      const double2 vv = ld_pair<TV>(V, (uint64_t)t * ld2 + i);
-      acc.x += s_coef[t] * vv.x;
-      acc.y += s_coef[t] * vv.y;
+      double vv[E];
+      ld_group<TV>(V, (uint64_t)t * ldg + i, vv);
+#pragma unroll
+      for (int e = 0; e < E; e++) acc[e] += s_coef[t] * vv[e];
     }
-    o2[i] = acc;
-    nacc += acc.x * acc.x;
-    nacc += acc.y * acc.y;
+#pragma unroll
+    for (int h = 0; h < E / 2; h++) o2[i * (E / 2) + h] = make_double2(acc[2 * h], acc[2 * h + 1]);
+#pragma unroll
+    for (int e = 0; e < E; e++) nacc += acc[e] * acc[e];
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    double acc = base ? base[n - 1] : 0.0;
-    for (uint32_t t = 0; t < nvec; t++) acc += s_coef[t] * (double)V[(uint64_t)t * ldv + n - 1];
-    out[n - 1] = acc;
-    nacc += acc * acc;
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (uint64_t r = ng * E; r < n; r++) {
+      double acc = base ? base[r] : 0.0;
+      for (uint32_t t = 0; t < nvec; t++) acc += s_coef[t] * (double)V[(uint64_t)t * ldv + r];
+      out[r] = acc;
+      nacc += acc * acc;
+    }
   if (norm2_out) {
     nacc = block_sum(nacc, sm);
     grid_sum_finish(nacc, partials, ticket, norm2_out, sm, &s_last);
@@ -1493,7 +1518,7 @@ int lz_k_norm2(lz_ctx* c, const double* v, uint64_t len, double* out) {
 
 int lz_k_multidot(lz_ctx* c, const void* V, bool f32, uint32_t nvec, const double* w, double* h_out, const int* skip) {
   unsigned g = (unsigned)c->sm_count * 4;
-  uint64_t want = (c->n_loc / 2 + kBlock) / kBlock;
+  uint64_t want = (c->n_loc / (f32 ? 4 : 2) + kBlock) / kBlock;
   if (want < g) g = (unsigned)(want ? want : 1);
   LZ_TRY(ensure_partials(c, (uint64_t)g * nvec));
   if (f32) k_multidot<float><<<g, kBlock, 0, c->stream>>>((const float*)V, c->ldv, nvec, w, c->n_loc, c->partials, c->ticket + 3, h_out, skip);

@@ -93,9 +93,17 @@ def main():
     assert ctx.exchange_info()[0] == lz.EXCHANGE_PEER_DENSE
     del os.environ["LZ_SPARSE_PUSH"]
     assert np.array_equal(yb, yd) and np.all(np.isfinite(yb))
-    # generated graph, compared with the CPU oracle
+    # generated graph, compared with the CPU oracle (multi-GPU contexts drop the original-order CSR unless asked to keep it)
     spec = lz.GraphSpec.rmat(16, 8, 1)
     ctx.graph_generate(spec)
+    try:
+        ctx.csr_download()
+        raise AssertionError("csr_download should have been refused")
+    except lz.LzError:
+        pass
+    os.environ["LZ_KEEP_CSR"] = "1"
+    ctx.graph_generate(spec)
+    del os.environ["LZ_KEEP_CSR"]
     ro, ci = ctx.csr_download()
     n = len(ro) - 1
     y = ctx.expv_host(None, 30)
