@@ -516,6 +516,39 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
     }
     return LZ_OK;
   }
+  if (!dist && reorth && c->lagged) {
+    // Full reorthogonalisation with the lagged normalisation (one GPU): the basis rows stay unnormalised (row j holds u_j, norm2v[j] =
+    // ||u_j||^2), the Gram-Schmidt coefficients are (u_t . w) / ||u_t||^2 (divided in k_multidot's last CTA) and the last k_combine
+    // of the step writes u_{j+1} straight into its basis row — the normalisation pass (k_scale: one launch, 16 n bytes) is gone.
+    c->lagged_run = true;
+    LZ_TRY(lz_k_fill(c, c->norm2v, 1, 1.0));
+    if (c->basis_f32) LZ_CUDA(cudaMemcpyAsync(c->ring[0], c->q0_64, ldv * 8, cudaMemcpyDeviceToDevice, c->stream));
+    int* skip = c->status + 1;
+    for (uint32_t j = 0; j < k; j++) {
+      double* uj = vec64(c, j);
+      {
+        Scope s(c, 0);
+        LZ_TRY(lz_k_spmv_dot(c, uj, uj, c->w, c->alpha + j, 0ull, nullptr, 0ull, c->norm2v + j));
+      }
+      if (j + 1 == k) break;
+      double* un = vec64(c, j + 1);
+      {  // three-term recurrence into the next basis row; ||.||^2 before the projections -> scal[3]
+        Scope s(c, 1);
+        LZ_TRY(lz_k_update_lagged(c, c->w, uj, j ? vec64(c, j - 1) : nullptr, c->alpha + j, c->norm2v + j, j ? c->norm2v + (j - 1) : nullptr,
+                                  un, c->scal + 3, c->beta + j, nullptr));
+      }
+      {
+        Scope s(c, 3);
+        LZ_TRY(lz_k_multidot(c, basis_ptr(c), c->basis_f32, j + 1, un, c->hcoef, nullptr, c->norm2v));
+        LZ_TRY(lz_k_combine(c, basis_ptr(c), c->basis_f32, j + 1, c->hcoef, -1.0, un, un, c->scal + 1, nullptr, vec32(c, j + 1)));
+        LZ_TRY(lz_k_reorth_decide(c, c->scal + 3, c->scal + 1, skip, reinterpret_cast<unsigned int*>(c->status + 2)));
+        LZ_TRY(lz_k_multidot(c, basis_ptr(c), c->basis_f32, j + 1, un, c->hcoef, skip, c->norm2v));
+        LZ_TRY(lz_k_combine(c, basis_ptr(c), c->basis_f32, j + 1, c->hcoef, -1.0, un, un, c->scal + 4, skip, vec32(c, j + 1)));
+        LZ_TRY(lz_k_reorth_select(c, skip, c->scal + 4, c->scal + 1, c->norm2v + (j + 1), c->beta + j));
+      }
+    }
+    return LZ_OK;
+  }
   if (dist && !reorth && c->lagged && c->peer_push && peer_scalars) {
     // Lagged normalisation over the peer exchange: SpMV passes + ONE kernel per step (k_update_lagged_push): it waits for
     // alpha, forms u_{j+1} and stores it straight into every rank's gathered vector; ||u_{j+1}||^2 is reduced off the

@@ -231,11 +231,12 @@ int lz_k_spread(lz_ctx* c, const double* local, double* xfull);
 int lz_k_collect(lz_ctx* c, const double* xfull, double* local);
 int lz_k_norm2(lz_ctx* c, const double* v, uint64_t len, double* out);
 // V: the basis, [nvec][ldv] doubles, or floats when f32 (LZ_BASIS_F32)
-int lz_k_multidot(lz_ctx* c, const void* V, bool f32, uint32_t nvec, const double* w, double* h_out /* device [nvec] */, const int* skip = nullptr);
+int lz_k_multidot(lz_ctx* c, const void* V, bool f32, uint32_t nvec, const double* w, double* h_out /* device [nvec] */, const int* skip = nullptr,
+                  const double* h_div = nullptr /* h[t] /= h_div[t]: unnormalised basis rows */);
 int lz_k_combine(lz_ctx* c, const void* V, bool f32, uint32_t nvec, const double* coef, double coef_sign, const double* base, double* out,
-                 double* norm2_out /* device scalar or null */, const int* skip = nullptr);
+                 double* norm2_out /* device scalar or null */, const int* skip = nullptr, float* out32 = nullptr /* fp32 copy of out */);
 int lz_k_reorth_decide(lz_ctx* c, const double* norm2_before, const double* norm2_after, int* skip, unsigned int* second_passes);
-int lz_k_reorth_select(lz_ctx* c, const int* skip, const double* norm2_second, double* norm2);
+int lz_k_reorth_select(lz_ctx* c, const int* skip, const double* norm2_second, double* norm2, double* norm2_copy = nullptr, double* beta_out = nullptr);
 int lz_k_tridiag_expv(lz_ctx* c, uint32_t k);
 int lz_k_tridiag_expv_into(lz_ctx* c, uint32_t k, double* eigvals, double* eigvecs, double* work, double* coef, int* status);
 // dst[i] = x_orig[new2old[first + i]] (/ sqrt(*norm2) when norm2 != null), i < count; padding slots -> 0

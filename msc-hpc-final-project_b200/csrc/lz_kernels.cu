@@ -1016,15 +1016,15 @@ constexpr int kDotTile = 8;
 template <class TV>
 __global__ void __launch_bounds__(kBlock) k_multidot(const TV* __restrict__ V, uint64_t ldv, uint32_t nvec, const double* __restrict__ w,
                                                      uint64_t n, double* partials /* [nvec][grid] */, unsigned int* ticket, double* h_out,
-                                                     const int* __restrict__ skip) {
+                                                     const int* __restrict__ skip, const double* __restrict__ h_div /* h[t] /= h_div[t], or null */) {
   constexpr int E = ept<TV>::value;
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
   if (skip && *skip) return;   // second Gram-Schmidt pass not needed (decided on the device, see k_reorth_decide)
   const uint64_t ng = n / E, ldg = ldv / E;         // whole 16-byte groups; the tail (n % E entries) is handled by thread 0 below
-  // w is re-read once per tile of T vectors. fp32 basis: a vector costs half the bytes, so the tile is twice as tall (16) to
-  // keep the re-read at 1/8 of the traffic; it is loaded in two batches of 8 x 16 bytes per thread.
-  constexpr int T = (E == 4) ? 2 * kDotTile : kDotTile;
+  // w is re-read once per tile of T vectors (fp64 basis: +1/8 of the traffic, fp32 basis: +1/4). A 16-vector tile for the fp32
+  // basis was measured slower (80 registers: C3 full reorth 487 vs 499 it/s), so both use 8.
+  constexpr int T = kDotTile;
   for (uint32_t t0 = 0; t0 < nvec; t0 += T) {
     double acc[T];
 #pragma unroll
@@ -1084,7 +1084,7 @@ __global__ void __launch_bounds__(kBlock) k_multidot(const TV* __restrict__ V, u
       double acc = 0.0;
       for (unsigned int i = lane; i < gridDim.x; i += 32) acc += __ldcg(partials + (uint64_t)t * gridDim.x + i);
       acc = warp_sum(acc);
-      if (lane == 0) h_out[t] = acc;
+      if (lane == 0) h_out[t] = h_div ? acc / h_div[t] : acc;   // unnormalised basis rows: (u_t . w) / ||u_t||^2
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }
@@ -1096,7 +1096,8 @@ __global__ void __launch_bounds__(kBlock) k_multidot(const TV* __restrict__ V, u
 template <class TV>
 __global__ void __launch_bounds__(kBlock) k_combine(const TV* __restrict__ V, uint64_t ldv, uint32_t nvec, const double* __restrict__ coef,
                                                     double sign, const double* base, double* out, uint64_t n, double* partials,
-                                                    unsigned int* ticket, double* norm2_out, const int* __restrict__ skip) {
+                                                    unsigned int* ticket, double* norm2_out, const int* __restrict__ skip,
+                                                    float* __restrict__ out32 /* fp32 copy of out, or null */) {
   constexpr int E = ept<TV>::value;
   extern __shared__ double s_coef[];
   __shared__ double sm[kWarps];
@@ -1133,6 +1134,10 @@ __global__ void __launch_bounds__(kBlock) k_combine(const TV* __restrict__ V, ui
     }
 #pragma unroll
     for (int h = 0; h < E / 2; h++) o2[i * (E / 2) + h] = make_double2(acc[2 * h], acc[2 * h + 1]);
+    if (out32) {
+#pragma unroll
+      for (int h = 0; h < E / 2; h++) reinterpret_cast<float2*>(out32)[i * (E / 2) + h] = make_float2((float)acc[2 * h], (float)acc[2 * h + 1]);
+    }
 #pragma unroll
     for (int e = 0; e < E; e++) nacc += acc[e] * acc[e];
   }
@@ -1141,6 +1146,7 @@ __global__ void __launch_bounds__(kBlock) k_combine(const TV* __restrict__ V, ui
       double acc = base ? base[r] : 0.0;
       for (uint32_t t = 0; t < nvec; t++) acc += s_coef[t] * (double)V[(uint64_t)t * ldv + r];
       out[r] = acc;
+      if (out32) out32[r] = (float)acc;
       nacc += acc * acc;
     }
   if (norm2_out) {
@@ -1297,8 +1303,11 @@ __global__ void k_reorth_decide(const double* __restrict__ norm2_before, const d
   if (need) atomicAdd(second_passes, 1u);
 }
 // norm2 = (second pass ran) ? norm2_second : unchanged
-__global__ void k_reorth_select(const int* __restrict__ skip, const double* __restrict__ norm2_second, double* __restrict__ norm2) {
+__global__ void k_reorth_select(const int* __restrict__ skip, const double* __restrict__ norm2_second, double* __restrict__ norm2,
+                                double* __restrict__ norm2_copy, double* __restrict__ beta_out) {
   if (!*skip) *norm2 = *norm2_second;
+  if (norm2_copy) *norm2_copy = *norm2;       // lagged normalisation: ||u_{j+1}||^2 and beta_j = ||u_{j+1}||
+  if (beta_out) *beta_out = sqrt(*norm2);
 }
 
 inline unsigned stream_grid(const lz_ctx* c, uint64_t work_items /* per-thread items */) {
@@ -1516,25 +1525,25 @@ int lz_k_norm2(lz_ctx* c, const double* v, uint64_t len, double* out) {
   return LZ_OK;
 }
 
-int lz_k_multidot(lz_ctx* c, const void* V, bool f32, uint32_t nvec, const double* w, double* h_out, const int* skip) {
+int lz_k_multidot(lz_ctx* c, const void* V, bool f32, uint32_t nvec, const double* w, double* h_out, const int* skip, const double* h_div) {
   unsigned g = (unsigned)c->sm_count * 4;
   uint64_t want = (c->n_loc / (f32 ? 4 : 2) + kBlock) / kBlock;
   if (want < g) g = (unsigned)(want ? want : 1);
   LZ_TRY(ensure_partials(c, (uint64_t)g * nvec));
-  if (f32) k_multidot<float><<<g, kBlock, 0, c->stream>>>((const float*)V, c->ldv, nvec, w, c->n_loc, c->partials, c->ticket + 3, h_out, skip);
-  else k_multidot<double><<<g, kBlock, 0, c->stream>>>((const double*)V, c->ldv, nvec, w, c->n_loc, c->partials, c->ticket + 3, h_out, skip);
+  if (f32) k_multidot<float><<<g, kBlock, 0, c->stream>>>((const float*)V, c->ldv, nvec, w, c->n_loc, c->partials, c->ticket + 3, h_out, skip, h_div);
+  else k_multidot<double><<<g, kBlock, 0, c->stream>>>((const double*)V, c->ldv, nvec, w, c->n_loc, c->partials, c->ticket + 3, h_out, skip, h_div);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
 
 int lz_k_combine(lz_ctx* c, const void* V, bool f32, uint32_t nvec, const double* coef, double coef_sign, const double* base, double* out,
-                 double* norm2_out, const int* skip) {
+                 double* norm2_out, const int* skip, float* out32) {
   unsigned g = stream_grid(c, c->n_loc / 2 + 1);
   LZ_TRY(ensure_partials(c, g));
   if (f32) k_combine<float><<<g, kBlock, nvec * sizeof(double), c->stream>>>((const float*)V, c->ldv, nvec, coef, coef_sign, base, out, c->n_loc,
-                                                                             c->partials, c->ticket + 4, norm2_out, skip);
+                                                                             c->partials, c->ticket + 4, norm2_out, skip, out32);
   else k_combine<double><<<g, kBlock, nvec * sizeof(double), c->stream>>>((const double*)V, c->ldv, nvec, coef, coef_sign, base, out, c->n_loc,
-                                                                          c->partials, c->ticket + 4, norm2_out, skip);
+                                                                          c->partials, c->ticket + 4, norm2_out, skip, out32);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
@@ -1545,8 +1554,8 @@ int lz_k_reorth_decide(lz_ctx* c, const double* norm2_before, const double* norm
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
-int lz_k_reorth_select(lz_ctx* c, const int* skip, const double* norm2_second, double* norm2) {
-  k_reorth_select<<<1, 1, 0, c->stream>>>(skip, norm2_second, norm2);
+int lz_k_reorth_select(lz_ctx* c, const int* skip, const double* norm2_second, double* norm2, double* norm2_copy, double* beta_out) {
+  k_reorth_select<<<1, 1, 0, c->stream>>>(skip, norm2_second, norm2, norm2_copy, beta_out);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }
