@@ -117,6 +117,39 @@ def ncu_traffic(workload, world):
     return None
 
 
+def step_breakdown(ctx, k, max_over_ranks):
+    """Mean microseconds per step of the phases inside the multi-GPU kernels (this rank; waits also as max over ranks)."""
+    ctx.trace_on(8192)
+    ctx.lanczos_run(k)
+    ev = ctx.trace_read(8192)
+    tag, t = ev[:, 0].astype(np.int64), ev[:, 1].astype(np.int64)
+    order = np.argsort(t, kind="stable")
+    tag, t = tag[order], t[order]
+    times = {}
+    for tg, ts in zip(tag, t):
+        times.setdefault((int(tg >> 8) & 255, int(tg & 255)), []).append(int(ts))
+
+    def mean_dur(kern, a, b):
+        x, y = times.get((kern, a), []), times.get((kern, b), [])
+        m = min(len(x), len(y))
+        if m < 4:
+            return None
+        d = (np.array(y[-m:]) - np.array(x[-m:]))[2:]
+        return float(np.mean(d)) / 1e3
+    out = {"update_wait_for_alpha": mean_dur(1, 1, 2), "update_push_chunk0": mean_dur(1, 2, 3), "update_kernel": mean_dur(1, 1, 4)}
+    passes = sorted({kern for kern, _ in times if kern >= 0x10})
+    for kern in passes:
+        b = kern - 0x10
+        out[f"spmv_pass{b}_wait_for_chunk"] = mean_dur(kern, 1, 2)
+        out[f"spmv_pass{b}_gather"] = mean_dur(kern, 2, 4)
+        out[f"spmv_pass{b}_senders_next_chunk"] = mean_dur(kern, 5, 6)
+    out = {k_: (round(v, 1) if v is not None else None) for k_, v in out.items()}
+    waits = [v for k_, v in out.items() if "wait" in k_ and v is not None]
+    out["wait_total_max_over_ranks"] = round(max_over_ranks(sum(waits)), 1) if waits else None
+    out["note"] = "rank 0; pass gather time of a non-final pass is that of its first gatherer CTA"
+    return out
+
+
 def workload_config(w, n, nnz, k, world):
     """The `config` object — identical in the `ours` and `reference` arms (same workload, same keys)."""
     n_loc, nnz_loc = n / world, nnz / world
@@ -361,6 +394,14 @@ def main():
     detail["iteration_frac_of_roofline"] = (k / (tm.lanczos_ms * 1e-3)) / (peak * 1e9 / b_iter) if tm.lanczos_ms else None
     b_mult = 8.0 * gi.n_local * k + 8.0 * gi.n_local
     detail["multout_gbs"] = b_mult / (tm.multout_ms * 1e-3) / 1e9 if tm.multout_ms else None
+
+    # several GPUs: where a step's time goes, from the device-side timeline of one extra (untimed) run — stream events cannot
+    # tell waiting for a peer apart from work inside the fused kernels (tools/trace_step.py prints the full table)
+    if world > 1:
+        try:
+            detail["step_breakdown_us"] = step_breakdown(ctx, k, max_over_ranks)
+        except Exception as e:                        # measurement hook only: never fail the bench line over it
+            detail["step_breakdown_us"] = {"error": str(e)[:200]}
 
     # the config's full-reorthogonalisation variant (BASELINE configs[2] "with full reorthogonalisation"): its own top-level
     # object with its own roofline (the Gram-Schmidt passes over the resident basis are HBM-bound GEMV-T + GEMV-N)

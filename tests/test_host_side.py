@@ -155,3 +155,30 @@ def test_c3_and_c2_reference_summaries_are_committed():
         g = np.load(p)
         assert len(g["alpha"]) == k and len(g["beta"]) == k - 1 and int(g["n"]) == 1 << scale
         assert float(g["top_gap"]) > 1e-6 and "ref_final" in str(g["meta"])
+
+
+def test_bench_step_breakdown_parses_a_device_timeline():
+    """bench.step_breakdown turns (tag, ns) events of lz_debug_trace into per-phase means; checked on a synthetic timeline."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    def tag(kern, phase):
+        return (kern << 8) | phase
+    ev, t = [], 1000
+    for step in range(8):
+        ev += [(tag(0x10, 1), t), (tag(0x10, 5), t), (tag(0x10, 2), t + 1000), (tag(0x10, 6), t + 90000), (tag(0x10, 4), t + 101000)]
+        t += 120000
+        ev += [(tag(0x11, 1), t), (tag(0x11, 2), t + 2000), (tag(0x11, 4), t + 60000)]
+        t += 65000
+        ev += [(tag(0x01, 1), t), (tag(0x01, 2), t + 9000), (tag(0x01, 3), t + 109000), (tag(0x01, 4), t + 130000)]
+        t += 135000
+
+    class FakeCtx:
+        def trace_on(self, cap): pass
+        def lanczos_run(self, k): pass
+        def trace_read(self, cap): return np.array(ev, dtype=np.uint64)
+    out = bench.step_breakdown(FakeCtx(), 8, lambda x: x)
+    assert out["update_wait_for_alpha"] == 9.0 and out["update_push_chunk0"] == 100.0 and out["update_kernel"] == 130.0
+    assert out["spmv_pass0_wait_for_chunk"] == 1.0 and out["spmv_pass0_gather"] == 100.0 and out["spmv_pass0_senders_next_chunk"] == 90.0
+    assert out["spmv_pass1_wait_for_chunk"] == 2.0 and out["spmv_pass1_senders_next_chunk"] is None
+    assert out["wait_total_max_over_ranks"] == 12.0
