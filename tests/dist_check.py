@@ -135,6 +135,27 @@ def main():
     assert all(b == ys[0] for b in ys)
     ctx.close()
     dist.barrier()
+    # the fallback paths behind the default (lagged loop over the peer exchange) stay in the library and stay tested:
+    # unlagged kernels over peer stores, scalars through NCCL, unfused push, and the chunked ncclAllGather exchange
+    gl = np.load(os.path.join(gdir, "rmat_s12_k30.npz"))
+    ro, ci, k, n = gl["row_offset"], gl["col_idx"], int(gl["k"]), int(gl["n"])
+    for env in ({"LZ_LAGGED_NORM": "0"}, {"LZ_PEER_SCALARS": "0"}, {"LZ_FUSED_PUSH": "0", "LZ_SPMV_COLBLOCKS": "3"},
+                {"LZ_PEER_PUSH": "0"}, {"LZ_PEER_PUSH": "0", "LZ_COMM_OVERLAP": "0", "LZ_SPMV_COLBLOCKS": "2"}):
+        os.environ.update(env)
+        box = [lz.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        c2 = lz.Context(local, rank, world, box[0])
+        c2.csr_upload(ro, ci)
+        y = c2.expv_host(None, k)
+        assert rel2(y, gl["ans"]) < 1e-9, (env, rel2(y, gl["ans"]))
+        assert np.array_equal(c2.top_k(100)[0], orc.top_k(gl["ans"])), env
+        if env.get("LZ_PEER_PUSH") == "0":
+            assert c2.exchange_info()[0] == lz.EXCHANGE_NCCL
+        assert rel2(c2.expv_host(None, k, lz.REORTH_FULL), gl["ans"]) < 1e-9, env
+        c2.close()
+        for key in env:
+            del os.environ[key]
+        dist.barrier()
     if rank == 0:
         print(f"DIST_OK {world}", flush=True)
     dist.destroy_process_group()
