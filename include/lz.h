@@ -10,7 +10,8 @@
  * Threading: one lz_ctx <-> one host thread <-> one GPU. Multi-GPU = one ctx per rank (process or thread), tied
  * together by an NCCL communicator created from lz_nccl_unique_id() (rank 0) + lz_create_dist() (all ranks).
  * All device work is enqueued on the ctx's own stream; nothing inside lz_lanczos_run / lz_tridiag_expv / lz_multout
- * synchronises with the host.
+ * synchronises with the host, except that the first lz_lanczos_run with a larger k than any before grows the basis (one
+ * allocation + stream sync before the loop; never inside it).
  *
  * Vertex order: callers always see the ORIGINAL vertex numbering (the one of the CSR / generator). Internally the
  * library relabels vertices (degree-descending, dealt cyclically over ranks); that permutation never leaks.
@@ -117,7 +118,7 @@ int lz_csr_download(lz_ctx* ctx, uint32_t* row_offset_out, uint32_t* col_idx_out
  *     footprint. All arithmetic stays fp64 and the three-term recurrence runs on fp64 copies of the last vectors, so alpha/beta of a
  *     plain run are those of the fp64 run; only the consumers of V see rounded vectors (error ~1e-8 relative, inside the 1e-6 the
  *     reference's own float build agrees with its double build to). This is what lanczosDecomp<float> (cu_lanczos.cu:144) maps to.
- *     One GPU per context only. */
+ *     With world > 1 every rank must select the same precision. */
 #define LZ_BASIS_F64 0
 #define LZ_BASIS_F32 1
 int lz_set_basis_precision(lz_ctx* ctx, int precision);

@@ -349,7 +349,7 @@ static int create_body(lz_ctx* c, int device, int rank, int world, const void* u
   if (const char* e = getenv("LZ_SPMV_VARIANT")) { int v = atoi(e); if (v >= 0 && v <= LZ_SPMV_WARP) c->spmv_variant = v; }     // tuning knob
   if (const char* e = getenv("LZ_SPMV_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) c->spmv_ctas_per_sm = (uint32_t)v; }   // tuning knob
   if (const char* e = getenv("LZ_LAGGED_NORM")) c->lagged = atoi(e) != 0;
-  if (const char* e = getenv("LZ_BASIS")) c->basis_f32 = world == 1 && (e[0] == 'f' || e[0] == 'F') && strstr(e, "32") != nullptr;   // "f32": experiments
+  if (const char* e = getenv("LZ_BASIS")) c->basis_f32 = (e[0] == 'f' || e[0] == 'F') && strstr(e, "32") != nullptr;   // "f32": experiments
   if (const char* e = getenv("LZ_PUSH_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 1024) c->push_ctas = (uint32_t)v; }        // tuning knob
   if (const char* e = getenv("LZ_SELL_GROUP")) { int v = atoi(e); if (v == 1 || v == 4) c->sell_group_force = (uint32_t)v; }      // test knob
   // watchdog of the in-kernel waits on peers (seconds; 0 = none). A trap poisons the CUDA context: the ctx must be destroyed.
@@ -433,7 +433,6 @@ extern "C" int lz_sync(lz_ctx* c) {
 
 extern "C" int lz_set_basis_precision(lz_ctx* c, int precision) {
   if (!c || (precision != LZ_BASIS_F64 && precision != LZ_BASIS_F32)) return lz_fail(LZ_ERR_ARG, "bad basis precision");
-  if (precision == LZ_BASIS_F32 && c->world > 1) return lz_fail(LZ_ERR_ARG, "the fp32 basis (LZ_BASIS_F32) is implemented for one GPU per context only");
   if ((precision == LZ_BASIS_F32) == c->basis_f32) return LZ_OK;
   LZ_TRY(set_dev(c));
   LZ_CUDA(cudaStreamSynchronize(c->stream));
@@ -554,10 +553,11 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
     // alpha, forms u_{j+1} and stores it straight into every rank's gathered vector; ||u_{j+1}||^2 is reduced off the
     // critical path. The gathered vector holds u_j unnormalised.
     LZ_TRY(lz_k_fill(c, c->norm2v, 1, 1.0));
+    if (c->basis_f32) LZ_CUDA(cudaMemcpyAsync(c->ring[0], c->q0_64, ldv * 8, cudaMemcpyDeviceToDevice, c->stream));
     const uint32_t push_chunks = fused_push ? 1u : c->ncolblk;
-    LZ_TRY(lz_k_scale_push(c, c->V, nullptr, c->V, nullptr, ++c->push_seq, push_chunks));   // q_0 (a previous run left its last vector there)
+    LZ_TRY(lz_k_scale_push(c, vec64(c, 0), nullptr, vec64(c, 0), nullptr, ++c->push_seq, push_chunks));   // q_0 (a previous run left its last vector there)
     for (uint32_t j = 0; j < k; j++) {
-      double* uj = c->V + (uint64_t)j * ldv;
+      double* uj = vec64(c, j);
       const double* q_dot = c->ncolblk == 1 ? c->xfull + (uint64_t)c->rank * c->chunk_rows : uj;
       ++c->red_seq;
       {
@@ -567,21 +567,22 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
       if (j + 1 == k) { LZ_TRY(lz_k_lagged_finish(c, j, c->red_seq)); break; }
       {
         Scope s(c, 1);
-        LZ_TRY(lz_k_update_lagged_push(c, c->w, uj, j ? uj - ldv : nullptr, uj + ldv, j, ++c->push_seq, push_chunks, c->red_seq));
+        LZ_TRY(lz_k_update_lagged_push(c, c->w, uj, j ? vec64(c, j - 1) : nullptr, vec64(c, j + 1), j, ++c->push_seq, push_chunks, c->red_seq,
+                                       vec32(c, j + 1)));
       }
     }
     c->lagged_run = true;
     return LZ_OK;
   }
+  if (c->basis_f32) LZ_CUDA(cudaMemcpyAsync(c->ring[0], c->q0_64, ldv * 8, cudaMemcpyDeviceToDevice, c->stream));
   if (dist) {   // q_0 into the gathered buffer (a previous run left q_{k-1} there)
     if (c->peer_push) {
-      LZ_TRY(lz_k_scale_push(c, c->V, nullptr, c->V, nullptr, ++c->push_seq, fused_push ? 1u : c->ncolblk));
+      LZ_TRY(lz_k_scale_push(c, vec64(c, 0), nullptr, vec64(c, 0), nullptr, ++c->push_seq, fused_push ? 1u : c->ncolblk));
     } else {
-      LZ_TRY(lz_k_spread(c, c->V, c->xfull));
+      LZ_TRY(lz_k_spread(c, vec64(c, 0), c->xfull));
       LZ_TRY(allgather_chunks(c, c->xfull, true));
     }
   }
-  if (c->basis_f32) LZ_CUDA(cudaMemcpyAsync(c->ring[0], c->q0_64, ldv * 8, cudaMemcpyDeviceToDevice, c->stream));
   for (uint32_t j = 0; j < k; j++) {
     double* qj = vec64(c, j);
     double* qprev = j ? vec64(c, j - 1) : nullptr;
@@ -623,9 +624,13 @@ static int enqueue_steps(lz_ctx* c, uint32_t k, int reorth, bool fused_push, boo
     if (!peer_scalars && !reorth) LZ_TRY(allreduce_sum(c, c->scal + 1, 1));
     {  // beta_j = ||w|| ; q_{j+1} = w / beta_j                            (cu_lanczos.cu:120-123)
       Scope s(c, 1);
-      if (c->peer_push) LZ_TRY(lz_k_scale_push(c, c->w, c->scal + 1, qnext, c->beta + j, ++c->push_seq, fused_push ? 1u : c->ncolblk,
-                                               peer_scalars ? c->red_seq : 0ull));
-      else LZ_TRY(lz_k_scale(c, c->w, c->scal + 1, qnext, dist ? c->xfull : nullptr, c->beta + j, vec32(c, j + 1)));
+      if (c->peer_push) {
+        LZ_TRY(lz_k_scale_push(c, c->w, c->scal + 1, qnext, c->beta + j, ++c->push_seq, fused_push ? 1u : c->ncolblk,
+                               peer_scalars ? c->red_seq : 0ull));
+        if (c->basis_f32) LZ_TRY(lz_k_convert(c, qnext, vec32(c, j + 1), nullptr, nullptr, c->n_loc));   // fp32 basis row
+      } else {
+        LZ_TRY(lz_k_scale(c, c->w, c->scal + 1, qnext, dist ? c->xfull : nullptr, c->beta + j, vec32(c, j + 1)));
+      }
     }
     if (!c->peer_push) LZ_TRY(allgather_chunks(c, c->xfull, true));
   }
@@ -644,7 +649,6 @@ extern "C" int lz_lanczos_run(lz_ctx* c, uint32_t k, int reorth) {
   if (reorth != LZ_REORTH_NONE && reorth != LZ_REORTH_FULL) return lz_fail(LZ_ERR_ARG, "bad reorth mode %d", reorth);
   if (!c->have_x) return lz_fail(LZ_ERR_ARG, "lz_set_start_vector must be called before lz_lanczos_run");
   LZ_TRY(set_dev(c));
-  if (c->basis_f32 && c->world > 1) return lz_fail(LZ_ERR_ARG, "the fp32 basis (LZ_BASIS_F32) is implemented for one GPU per context only");
   LZ_TRY(ensure_k(c, k));
   // chunk 0 of each new vector is sent by the normalisation kernel, chunk b + 1 by SpMV pass b (sliced variant only)
   bool fused_push = c->peer_push && !c->sparse_push && c->spmv_variant == LZ_SPMV_AUTO && c->ncolblk > 1;

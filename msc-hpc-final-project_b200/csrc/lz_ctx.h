@@ -210,7 +210,7 @@ int lz_k_update_lagged(lz_ctx* c, const double* t, const double* uj, const doubl
 int lz_k_convert(lz_ctx* c, const double* src64, float* dst32, const float* src32, double* dst64, uint64_t n);
 // lagged normalisation on several GPUs (peer exchange + peer scalars): see k_update_lagged_push
 int lz_k_update_lagged_push(lz_ctx* c, const double* t, const double* uj, const double* uprev, double* u_next, uint32_t j,
-                            unsigned long long push_seq, uint32_t push_chunks, unsigned long long red_seq);
+                            unsigned long long push_seq, uint32_t push_chunks, unsigned long long red_seq, float* u32_next = nullptr);
 int lz_k_lagged_finish(lz_ctx* c, uint32_t j, unsigned long long red_seq);
 int lz_k_set_trace(lz_ctx* c, unsigned long long* buf_device);   // device timeline on (buffer) / off (null)
 int lz_k_set_peer_timeout(lz_ctx* c, double seconds);   // watchdog of the in-kernel peer waits; <= 0 disables it

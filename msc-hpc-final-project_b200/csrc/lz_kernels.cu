@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(kBlock) k_update_lagged_push(const double* __r
                                                                const __grid_constant__ lz_peers peers, uint64_t cl, uint32_t nchunks, uint32_t push_chunks,
                                                                uint32_t world, uint32_t rank, unsigned long long push_seq, unsigned int* push_ticket,
                                                                double* partials, unsigned int* ticket, const __grid_constant__ lz_red red,
-                                                               const __grid_constant__ lz_push_lists lists) {
+                                                               const __grid_constant__ lz_push_lists lists, float* __restrict__ u32_next) {
   __shared__ double sm[kWarps];
   __shared__ bool s_last;
   __shared__ double s_bcast;
@@ -783,6 +783,7 @@ __global__ void __launch_bounds__(kBlock) k_update_lagged_push(const double* __r
       v.x = lagged_entry(tv.x, qv.x, pv.x, a, rj, cp, up != nullptr);
       v.y = lagged_entry(tv.y, qv.y, pv.y, a, rj, cp, up != nullptr);
       o2[li] = v;
+      if (u32_next) reinterpret_cast<float2*>(u32_next)[li] = make_float2((float)v.x, (float)v.y);   // fp32 basis row
       acc = fma(v.x, v.x, acc);
       acc = fma(v.y, v.y, acc);
       if (SPARSE) reinterpret_cast<double2*>(own)[slot2 + i] = v;
@@ -1454,7 +1455,7 @@ int lz_k_update_lagged(lz_ctx* c, const double* t, const double* uj, const doubl
   return LZ_OK;
 }
 int lz_k_update_lagged_push(lz_ctx* c, const double* t, const double* uj, const double* uprev, double* u_next, uint32_t j,
-                            unsigned long long push_seq, uint32_t push_chunks, unsigned long long red_seq) {
+                            unsigned long long push_seq, uint32_t push_chunks, unsigned long long red_seq, float* u32_next) {
   lz_peers peers;
   for (int r = 0; r < LZ_MAX_WORLD; r++) { peers.x[r] = c->peer_xfull[r]; peers.f[r] = c->peer_flags[r]; }
   lz_push_lists lists;
@@ -1467,7 +1468,8 @@ int lz_k_update_lagged_push(lz_ctx* c, const double* t, const double* uj, const 
   LZ_TRY(ensure_partials(c, g));
   auto kern = c->sparse_push ? k_update_lagged_push<true> : k_update_lagged_push<false>;
   kern<<<g, kBlock, 0, c->stream>>>(t, uj, uprev, c->n_loc, u_next, c->norm2v, j, c->alpha, c->beta, peers, c->chunk_rows, c->ncolblk, push_chunks,
-                                    (uint32_t)c->world, (uint32_t)c->rank, push_seq, c->push_ticket, c->partials, c->ticket + 1, make_red(c, red_seq), lists);
+                                    (uint32_t)c->world, (uint32_t)c->rank, push_seq, c->push_ticket, c->partials, c->ticket + 1, make_red(c, red_seq), lists,
+                                    u32_next);
   LZ_LAUNCH_CHECK();
   return LZ_OK;
 }

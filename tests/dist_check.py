@@ -156,6 +156,34 @@ def main():
         for key in env:
             del os.environ[key]
         dist.barrier()
+    # fp32-basis mode on several GPUs (V stored as floats, recurrence on fp64 copies): alpha/beta bit-equal to the fp64-basis run,
+    # e^A x within the reference's own float-vs-double agreement, plain / reorthogonalised / needed-columns exchange
+    fl = np.load(os.path.join(gdir, "reference_float.npz"))
+    for name, env in (("rmat_s14_k50", {}), ("band_n4096_k40", {"LZ_SPARSE_PUSH": "1", "LZ_ORDER": "n"}), ("c1_er_n10000_k20", {"LZ_LAGGED_NORM": "0"})):
+        gl = np.load(os.path.join(gdir, name + ".npz"))
+        ro, ci, k, n = gl["row_offset"], gl["col_idx"], int(gl["k"]), int(gl["n"])
+        os.environ.update(env)
+        box = [lz.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        c3 = lz.Context(local, rank, world, box[0])
+        c3.csr_upload(ro, ci)
+        y64 = c3.expv_host(None, k)
+        a64, b64 = c3.get_tridiag()
+        c3.set_basis_precision(lz.BASIS_F32)
+        y32 = c3.expv_host(None, k)
+        a32, b32 = c3.get_tridiag()
+        d_ref = float(fl[name + "__ref_f32_vs_f64"])
+        assert np.array_equal(a32, a64) and np.array_equal(b32, b64), name
+        assert rel2(y32, gl["ans"]) < min(0.1 * d_ref, 1e-6), (name, rel2(y32, gl["ans"]), d_ref)
+        assert rel2(c3.expv_host(None, k, lz.REORTH_FULL), gl["ans"]) < 1e-6, name
+        q = c3.get_basis(k - 1)
+        assert abs(q @ q - 1) < 1e-6
+        c3.set_basis_precision(lz.BASIS_F64)
+        assert np.array_equal(c3.expv_host(None, k), y64), name
+        c3.close()
+        for key in env:
+            del os.environ[key]
+        dist.barrier()
     if rank == 0:
         print(f"DIST_OK {world}", flush=True)
     dist.destroy_process_group()

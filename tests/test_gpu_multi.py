@@ -32,6 +32,7 @@ def test_cpp_driver_threads_per_gpu(lz, tmp_path):
     ref, _, _ = orc.expv(ro, ci, 25, np.ones(n))
     ans = str(tmp_path / "ref.f64")
     ref.tofile(ans)
-    r = subprocess.run([os.path.join(libdir, "final"), "--graph", "rmat", "--scale", "15", "--ef", "8", "--seed", "1", "-k", "25",
-                        "--gpus", "2", "--check", ans], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for extra in ([], ["--reorth"]):      # --reorth: the coefficient reductions go through NCCL from two host threads of one process
+        r = subprocess.run([os.path.join(libdir, "final"), "--graph", "rmat", "--scale", "15", "--ef", "8", "--seed", "1", "-k", "25",
+                            "--gpus", "2", "--check", ans] + extra, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
