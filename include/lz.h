@@ -15,6 +15,10 @@
  *
  * Vertex order: callers always see the ORIGINAL vertex numbering (the one of the CSR / generator). Internally the
  * library relabels vertices (degree-descending, dealt cyclically over ranks); that permutation never leaks.
+ *
+ * Environment knobs (read at lz_create / graph load; all optional, for tuning and tests): LZ_SPMV_VARIANT, LZ_SPMV_CTAS,
+ * LZ_SPMV_WINDOW_MB, LZ_SPMV_COLBLOCKS, LZ_ORDER (d|n), LZ_LAGGED_NORM, LZ_BASIS (f32), LZ_PUSH_CTAS, LZ_PEER_PUSH,
+ * LZ_PEER_SCALARS, LZ_FUSED_PUSH, LZ_SPARSE_PUSH, LZ_COMM_OVERLAP, LZ_PEER_TIMEOUT_S, LZ_KEEP_CSR, LZ_SHARDED_INGEST, LZ_CUDA_GRAPH.
  */
 #ifndef LZ_H_B200
 #define LZ_H_B200
