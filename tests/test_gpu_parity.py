@@ -408,6 +408,23 @@ def test_unlagged_loop_still_matches(lz, orc, golden, monkeypatch, basis):
         assert np.all(np.isfinite(alpha)) and np.all(beta > 0)
 
 
+def test_analytic_eigen_combination(lz, orc, ctx):
+    """The reference's analytic test method (serial/tests/numerical_test.cc:74-116; tests/test_oracle.py builds the same problem
+    for the oracle): x is a combination of 100 eigenvectors of A, so e^A x is known in closed form. Recorded behaviour of the
+    reference (serial/output/numerical_test_output.txt): useless at k = 5, 3.5e-11 at k = 20, 4e-15 at k = 25."""
+    from test_oracle import analytic_eigen_combination
+    n, ro, ci = lz.generate_host(lz.GraphSpec.er(1500, 6000, 17))
+    x, y = analytic_eigen_combination(ro, ci)
+    ctx.csr_upload(ro, ci)
+    rel = {}
+    for k in (5, 10, 20, 30):
+        rel[k] = rel2(ctx.expv_host(x, k), y)
+        ans_o, _, _ = orc.expv(ro, ci, k, x)
+        assert rel2(ctx.expv_host(x, k), ans_o) < TOL
+    assert rel[5] > 1e-3 and 1e-8 < rel[10] < 1e-4 and rel[20] < 1e-11 and rel[30] < 1e-11, rel
+    assert rel2(ctx.expv_host(x, 30, lz.REORTH_FULL), y) < 1e-11
+
+
 def test_cpp_api_driver_matches_reference_golden(lz, golden, tmp_path):
     """The C++ mirror of the reference API (lib/final: adjMatrix -> lanczosDecomp -> eigenDecomp -> multOut) reproduces the
     reference's answer through the reference's own text format."""

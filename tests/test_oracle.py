@@ -210,3 +210,32 @@ def test_oracle_regular_graph_with_nonconstant_x(orc):
     assert rel2(y, V @ (np.exp(w) * (V.T @ x))) < 1e-10
     y1, _, _ = orc.expv(ro, ci, 5, np.ones(n))          # the documented breakdown: not finite, and not silently "fixed"
     assert not np.all(np.isfinite(y1))
+
+
+def analytic_eigen_combination(ro, ci, n_pairs=100, seed=1234):
+    """The reference's own analytic test method (serial/tests/numerical_test.cc:74-116): x = sum_i c_i v_i over `n_pairs`
+    eigenpairs of A with c_i ~ U(0,1), so that e^A x = sum_i c_i e^{lambda_i} v_i exactly. The reference read MATLAB-computed
+    eigenpairs from data files that are not in the repository; here they come from a dense symmetric eigensolver."""
+    n = len(ro) - 1
+    A = np.zeros((n, n))
+    rows = np.repeat(np.arange(n), np.diff(ro))
+    A[rows, ci] = 1.0
+    w, V = np.linalg.eigh(A)
+    pick = np.argsort(-np.abs(w))[:n_pairs]                   # "the first 100 eigenpairs": largest magnitude, as MATLAB's eigs returns
+    c = np.random.default_rng(seed).random(n_pairs)
+    x = V[:, pick] @ c
+    y = V[:, pick] @ (c * np.exp(w[pick]))
+    return x, y
+
+
+def test_oracle_analytic_eigen_combination(lz, orc):
+    """Same construction and the same behaviour as the reference's recorded outcomes (serial/output/numerical_test_output.txt:
+    useless at k = 5, 3.5e-11 at k = 20, 4e-15 at k = 25 on its 2114-vertex graph): the error falls steeply with k."""
+    n, ro, ci = lz.generate_host(lz.GraphSpec.er(1500, 6000, 17))
+    x, y = analytic_eigen_combination(ro, ci)
+    rel = {}
+    for k in (5, 20, 30, 45):
+        ans, _, _ = orc.expv(ro, ci, k, x)
+        rel[k] = np.linalg.norm(ans - y) / np.linalg.norm(y)
+    assert rel[5] > 1e-3 and rel[20] < 1e-6 and rel[30] < 1e-10 and rel[45] < 1e-11, rel
+    assert rel[5] > rel[20] > rel[30]
