@@ -2,8 +2,10 @@
 // multOut, read-back, test hooks and timing. Host orchestration only; kernels are in lz_kernels.cu.
 //
 // The driver loop replaces lanczosDecomp<T>::cu_decompose (reference parallel-final/lib/cu_lanczos.cu:97-128), which
-// issues 8 launches + one D2H copy of q_j per step on three streams. Here one step is 3 launches (2 on the last step),
-// the basis never leaves HBM, and multi-GPU steps add one in-place ncclAllGather + two scalar ncclAllReduce.
+// issues 8 launches + one D2H copy of q_j per step on three streams. Here one step is the SpMV passes (one per column block)
+// plus ONE vector kernel, on one GPU and on several; the basis never leaves HBM, and the multi-GPU exchange and scalar
+// reductions are peer stores / peer-memory slots fused into those kernels (NCCL only as fallback, for the reorthogonalisation
+// coefficients and for the rendezvous that opens a run).
 #include "lz_ctx.h"
 
 #include <dlfcn.h>

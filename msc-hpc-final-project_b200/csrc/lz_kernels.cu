@@ -1,18 +1,23 @@
 // lz_kernels.cu — hand-written sm_100a kernels of the Lanczos e^A·x hot path. Every kernel is HBM/L2-bandwidth bound
 // fp64 streaming or gather work (<= 0.25 flop/byte): no tensor-core shapes anywhere.
 //
-//   k_spmv_dot      w = A x  (value-less CSR gather-sum) fused with the partial of alpha = w . q_j
-//                   replaces cu_spMV1 + cu_dot_prod + cu_reduce (reference parallel-final/lib/cu_SPMV.cu:31-41,
-//                   cu_linalg.cu:67-131; launches at cu_lanczos.cu:101-105)
-//   k_update_norm   w -= alpha q_j ; w -= beta_{j-1} q_{j-1} ; partial of ||w||^2          (one pass)
-//                   replaces cu_dpax x2 + cu_norm_sq + cu_reduce_sqrt (cu_linalg.cu:223-226,184-208,146-170; cu_lanczos.cu:108-120)
-//   k_scale         q_{j+1} = w / beta_j  written straight into the resident basis (and the all-gather slot)
-//                   replaces cu_dvexda (cu_linalg.cu:241-244; cu_lanczos.cu:123) and the per-step D2H of q_j (:126)
+//   k_spmv_sell / k_spmv_dot   w = A x  (value-less gather-sum; sliced-ELLPACK default, CSR variants) fused with the partial of
+//                   alpha = w . q_j; on several GPUs also the consumer (acquire-spin on chunk arrival) and, through a few sender
+//                   CTAs, the producer of the NVLink exchange. Replaces cu_spMV1 + cu_dot_prod + cu_reduce (reference
+//                   parallel-final/lib/cu_SPMV.cu:31-41, cu_linalg.cu:67-131; launches at cu_lanczos.cu:101-105)
+//   k_update_lagged            one GPU: u_{j+1} = (t - alpha u_j)/||u_j|| - (||u_j||/||u_{j-1}||) u_{j-1}, partial of ||u_{j+1}||^2 — ONE pass;
+//                   the normalisation is lagged into the consumers. Replaces cu_dpax x2 + cu_norm_sq + cu_reduce_sqrt + cu_dvexda
+//                   (cu_linalg.cu:223-226,184-208,146-170,241-244; cu_lanczos.cu:108-123) and the per-step D2H of q_j (:126)
+//   k_update_lagged_push       several GPUs: the same pass fused with both cross-GPU scalar reductions (peer memory) and with the
+//                   peer stores of u_{j+1} into every rank's gathered vector (whole chunks, or entry-wise for band-like graphs).
+//                   Generalises parallel-two-cards/lib/cu_lanczos.cu:116-165
+//   k_update_norm, k_scale, k_scale_push[_sparse]   the reference-shaped two-kernel step (fallback paths, multi-GPU reorthogonalisation)
 //   k_multidot      h = V_j^T w   (tall-skinny GEMV-T) for full reorthogonalisation (precedent: serial/lib/lanczos.cc:85-91)
-//   k_combine       out = base + s * V^T-combination: reorth update  w -= V h  and  multOut  ans = V c
+//   k_combine       out = base + s * V^T-combination: reorth update  w -= V h  and  multOut  ans = V c; fp64 or fp32 basis rows
 //                   replaces cblas_dgemv / cublasDgemv (multiplyOut.cu:43-47, parallel-mult-on-card/lib/cu_multiplyOut.cu:66-72)
 //   k_tridiag_expv  eigen-decomposition of the k x k tridiagonal (implicit-shift QL) + c = ||x|| Z (e^lambda . Z^T e1)
 //                   replaces LAPACKE_dstevd (eigen.cu:17-21) and multiplyOut.cu:30-40
+// (the ranking kernels are in lz_rank.cu, graph construction in lz_graph.cu)
 //
 // All grid-wide reductions are deterministic: per-CTA partials in a fixed slot, summed in a fixed order by the last CTA
 // to finish (ticket counter), result left in device memory so the next kernel reads it without a host round-trip —
