@@ -73,28 +73,40 @@ __global__ void __launch_bounds__(kRankBlock) k_rank_pass(const double* __restri
   __syncthreads();
   const unsigned long long pre_hi = st->pre_hi;
   const unsigned pre_lo = st->pre_lo;
-  const uint64_t n_round = (n_loc + 31) & ~31ull;             // whole warps stay converged for __match_any_sync
-  for (uint64_t l = (uint64_t)blockIdx.x * kRankBlock + threadIdx.x; l < n_round; l += (uint64_t)gridDim.x * kRankBlock) {
-    bool take = false;
-    unsigned dig = 0;
-    if (l < n_loc) {
-      const uint32_t o = __ldg(new2old + slot_of(l, cl, world, rank));
-      if (o != 0xFFFFFFFFu) {
-        const unsigned long long hi = value_key(ans[l]);
-        take = prefix_match(hi, ~o, d, pre_hi, pre_lo);
-        dig = digit_of(hi, ~o, d);
-      }
+  const uint64_t n_round = (n_loc + 31) & ~31ull;             // whole warps stay converged for the ballots
+  const uint64_t stride = (uint64_t)gridDim.x * kRankBlock;
+  constexpr int kUnroll = 4;                                   // 4 independent (index, value) loads in flight per thread: the ballot
+                                                               // would otherwise serialise the loop on memory latency (100 us per pass)
+  for (uint64_t l0 = (uint64_t)blockIdx.x * kRankBlock + threadIdx.x; l0 < n_round; l0 += kUnroll * stride) {
+    uint32_t o[kUnroll];
+    double a[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      const uint64_t l = l0 + u * stride;
+      o[u] = l < n_loc ? __ldg(new2old + slot_of(l, cl, world, rank)) : 0xFFFFFFFFu;
+      a[u] = l < n_loc ? __ldcs(ans + l) : 0.0;
     }
-    // In the first passes every entry matches and most share a digit: aggregate per warp (one atomic per distinct digit). Later
-    // passes have a handful of takers at most: plain shared-memory atomics, and no __match_any (its cost grows with the number
-    // of distinct values in the warp: 160 us per pass with 32 distinct non-participant classes, measured).
-    const unsigned takers = __ballot_sync(0xffffffffu, take);
-    if (take) {
-      if (__popc(takers) >= 8) {
-        const unsigned peers = __match_any_sync(takers, dig);      // exactly the takers execute this, with their own mask
-        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[dig], (unsigned)__popc(peers));
-      } else {
-        atomicAdd(&sh[dig], 1u);
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      if (l0 + u * stride >= n_round) break;                   // warp-uniform: l0 is lane-contiguous and n_round a multiple of 32
+      bool take = false;
+      unsigned dig = 0;
+      if (o[u] != 0xFFFFFFFFu) {
+        const unsigned long long hi = value_key(a[u]);
+        take = prefix_match(hi, ~o[u], d, pre_hi, pre_lo);
+        dig = digit_of(hi, ~o[u], d);
+      }
+      // In the first passes every entry matches and most share a digit: aggregate per warp (one atomic per distinct digit). Later
+      // passes have a handful of takers at most: plain shared-memory atomics, and no __match_any (its cost grows with the number
+      // of distinct values in the warp: 160 us per pass with 32 distinct non-participant classes, measured).
+      const unsigned takers = __ballot_sync(0xffffffffu, take);
+      if (take) {
+        if (__popc(takers) >= 8) {
+          const unsigned peers = __match_any_sync(takers, dig);      // exactly the takers execute this, with their own mask
+          if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[dig], (unsigned)__popc(peers));
+        } else {
+          atomicAdd(&sh[dig], 1u);
+        }
       }
     }
   }
