@@ -92,8 +92,8 @@ __device__ __forceinline__ void red_publish(const lz_red& red, int kind, double 
   const size_t idx = ((size_t)kind * 2 + (red.seq & 1)) * LZ_MAX_WORLD + red.rank;
   for (uint32_t r = 0; r < red.world; r++) red.area[r][idx].val = v;      // all values first ...
   __threadfence_system();                                                 // ... one fence ...
-  for (uint32_t r = 0; r < red.world; r++)                                // ... then the sequence numbers
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&red.area[r][idx].seq), "l"(red.seq) : "memory");
+  for (uint32_t r = 0; r < red.world; r++)                                // ... then the sequence numbers (relaxed: the fence is the release)
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&red.area[r][idx].seq), "l"(red.seq) : "memory");
 }
 // All threads of the CTA call this; returns the total of reduction `seq` of `kind` in every thread.
 __device__ __forceinline__ double red_consume_seq(const lz_red& red, int kind, unsigned long long seq, double* sm_bcast) {
@@ -186,8 +186,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// Flag / sequence-number store of the release pattern "fence.acq_rel.sys ; st.relaxed.sys": every caller issues ONE
+// __threadfence_system() after its data stores and then publishes to all ranks with relaxed system-scope stores. A
+// st.release.sys per destination would repeat the fence (SASS: MEMBAR.ALL.SYS before every STG.STRONG.SYS — 8 serialised
+// system-wide barriers by one thread on the critical path of every chunk arrival at 8 GPUs).
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // Consumer side: block until chunk `blk` of the gathered vector has been written by every rank (counter >= seq).
@@ -233,7 +237,7 @@ __device__ __forceinline__ void push_chunk(const double* __restrict__ src, const
     if (*s_flag) {
       ticket[c] = 0u;
       __threadfence_system();
-      for (uint32_t r = 0; r < world; r++) st_release_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, seq);
+      for (uint32_t r = 0; r < world; r++) st_relaxed_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, seq);
     }
   }
   __syncthreads();
@@ -804,7 +808,7 @@ __global__ void __launch_bounds__(kBlock) k_update_lagged_push(const double* __r
       if (s_last) {
         push_ticket[c] = 0u;
         __threadfence_system();
-        for (uint32_t r = 0; r < world; r++) st_release_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, push_seq);
+        for (uint32_t r = 0; r < world; r++) st_relaxed_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, push_seq);
         trace_mark(LZ_TR(0x01, TR_PUSHED));
       }
     }
@@ -833,7 +837,7 @@ __global__ void __launch_bounds__(kBlock) k_update_lagged_push(const double* __r
         *push_ticket = 0u;
         __threadfence_system();
         for (uint32_t c = 0; c < nchunks; c++)
-          for (uint32_t r = 0; r < world; r++) st_release_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, push_seq);
+          for (uint32_t r = 0; r < world; r++) st_relaxed_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, push_seq);
       }
     }
     __syncthreads();
@@ -938,7 +942,7 @@ __global__ void __launch_bounds__(kBlock) k_scale_push(const double* __restrict_
       if (s_last) {
         ticket[c] = 0u;
         __threadfence_system();
-        for (uint32_t r = 0; r < world; r++) st_release_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, seq);
+        for (uint32_t r = 0; r < world; r++) st_relaxed_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, seq);
       }
     }
     __syncthreads();
@@ -989,7 +993,7 @@ __global__ void __launch_bounds__(kBlock) k_scale_push_sparse(const double* __re
       *ticket = 0u;
       __threadfence_system();
       for (uint32_t c = 0; c < nchunks; c++)
-        for (uint32_t r = 0; r < world; r++) st_release_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, seq);
+        for (uint32_t r = 0; r < world; r++) st_relaxed_sys(peers.f[r] + (uint64_t)c * LZ_MAX_WORLD + rank, seq);
     }
   }
 }
