@@ -268,7 +268,7 @@ def main():
         orc = graft.load_oracle()              # the oracle is only ever loaded for the reference / cpu_baseline legs
         csr_path = os.path.join(tempfile.gettempdir(), f"lz_bench_{args.workload}_{args.scale or ''}_{os.getpid()}.bin")
         n, nnz = make_csr_file(w, args.scale, args.n, csr_path, local_rank)     # input construction: separate process, untimed
-        m = sample_iters_for(nnz)
+        m = min(sample_iters_for(nnz), k)             # never more steps than the config's Krylov dimension
         total = args.steps + args.warmup
         vals, secs, kind, a_ref, b_ref = cpu_reference_sample(orc, csr_path, n, nnz, m, reps=total)
         os.unlink(csr_path)
@@ -526,7 +526,7 @@ def main():
         orc = graft.load_oracle()
         csr_path = os.path.join(tempfile.gettempdir(), f"lz_bench_{args.workload}_{os.getpid()}.bin")
         make_csr_file(w, args.scale, args.n, csr_path, local_rank)
-        m = sample_iters_for(nnz)
+        m = min(sample_iters_for(nnz), k)             # never more steps than the config's Krylov dimension
         vals, secs, kind, a_ref, b_ref = cpu_reference_sample(orc, csr_path, n, nnz, m, reps=1)
         os.unlink(csr_path)
         cpu = {"value": vals[0], "unit": UNIT, "cores": 1, "kind": kind,
