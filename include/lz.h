@@ -80,7 +80,9 @@ int lz_csr_from_edges(uint64_t n, uint64_t n_edges, const uint32_t* u, const uin
                       uint32_t** row_offset_out, uint32_t** col_idx_out);
 
 /* Reference text format ("n n E" header, then E lines "col row", 1-based, upper-triangle entries once):
- * adjMatrix::populate_sparse_matrix (parallel-final/lib/adjMatrix.cc:21-46) and write_matrix_to_file (:53-69). */
+ * adjMatrix::populate_sparse_matrix (parallel-final/lib/adjMatrix.cc:21-46) and write_matrix_to_file (:53-69). That format is a
+ * MatrixMarket coordinate file with its banner stripped (serial/README.md:9); the reader also accepts the unstripped file:
+ * '%' comment lines are skipped and a value column is ignored (the matrix is pattern-only either way). */
 int lz_csr_read_text(const char* path, uint64_t* n_out, uint64_t* nnz_out, uint32_t** row_offset_out, uint32_t** col_idx_out);
 int lz_csr_write_text(const char* path, uint64_t n, const uint32_t* row_offset, const uint32_t* col_idx);
 /* Binary CSR cache ("LZCSR1\0\0", u64 n, u64 nnz, u32 row_offset[n+1], u32 col_idx[nnz]); also what oracle/_ref/ref_final --csr reads. */

@@ -85,13 +85,28 @@ extern "C" int lz_csr_from_edges(uint64_t n, uint64_t n_edges, const uint32_t* u
   }
 }
 
+// Next line that carries data: skips blank lines and '%' comment lines (MatrixMarket banner / comments). Returns false at EOF.
+static bool next_data_line(FILE* f, char* buf, size_t cap) {
+  while (fgets(buf, (int)cap, f)) {
+    const char* p = buf;
+    while (*p == ' ' || *p == '\t') p++;
+    if (*p == '%' || *p == '\n' || *p == '\r' || *p == 0) continue;
+    return true;
+  }
+  return false;
+}
+
 extern "C" int lz_csr_read_text(const char* path, uint64_t* n_out, uint64_t* nnz_out, uint32_t** row_offset_out,
                                 uint32_t** col_idx_out) {
   if (!path || !n_out || !nnz_out || !row_offset_out || !col_idx_out) return lz_fail(LZ_ERR_ARG, "null argument");
   FILE* f = fopen(path, "r");
   if (!f) return lz_fail(LZ_ERR_IO, "cannot open %s", path);
+  // The reference's format is a MatrixMarket coordinate file with the banner stripped (serial/README.md:9): "n n E", then E lines
+  // "col row". The same reader therefore also takes the unstripped file: '%' lines are skipped and anything after the two indices
+  // of an entry line (a value column) is ignored — the matrix is pattern-only either way.
+  char line[512];
   unsigned long long n = 0, n2 = 0, e = 0;
-  if (fscanf(f, "%llu %llu %llu", &n, &n2, &e) != 3 || n == 0 || n > 0xFFFFFFFFull) {
+  if (!next_data_line(f, line, sizeof line) || sscanf(line, "%llu %llu %llu", &n, &n2, &e) != 3 || n == 0 || n != n2 || n > 0xFFFFFFFFull) {
     fclose(f);
     return lz_fail(LZ_ERR_IO, "%s: bad header (expected 'n n E')", path);
   }
@@ -105,7 +120,10 @@ extern "C" int lz_csr_read_text(const char* path, uint64_t* n_out, uint64_t* nnz
     keys.reserve(2 * (e < max_edges ? e : max_edges));
     for (unsigned long long i = 0; i < e; i++) {
       unsigned long long col, row;
-      if (fscanf(f, "%llu %llu", &col, &row) != 2) { fclose(f); return lz_fail(LZ_ERR_IO, "%s: short edge list (%llu of %llu)", path, i, e); }
+      if (!next_data_line(f, line, sizeof line) || sscanf(line, "%llu %llu", &col, &row) != 2) {
+        fclose(f);
+        return lz_fail(LZ_ERR_IO, "%s: short edge list (%llu of %llu)", path, i, e);
+      }
       if (col < 1 || row < 1 || col > n || row > n) { fclose(f); return lz_fail(LZ_ERR_IO, "%s: vertex out of range on edge %llu", path, i); }
       --col; --row;                                   // files are 1-based (adjMatrix.cc:31-34)
       keys.push_back(((uint64_t)row << 32) | col);    // both triangles, duplicates collapse in the builder

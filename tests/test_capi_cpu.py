@@ -98,3 +98,27 @@ def test_gpu_entry_points_fail_loudly_without_a_device(lz):
     with pytest.raises(lz.LzError) as e:
         lz.Context(0)
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_text_reader_accepts_matrix_market_files(lz, tmp_path):
+    """The reference's input format is MatrixMarket 'coordinate' with the banner stripped (serial/README.md:9). The reader takes
+    both: '%' lines are skipped, a value column is ignored; stripped and unstripped files give the same CSR."""
+    import numpy as np
+    n, ro, ci = lz.generate_host(lz.GraphSpec.er(300, 900, 4))
+    plain, mm = str(tmp_path / "g.txt"), str(tmp_path / "g.mtx")
+    lz.write_text(plain, ro, ci)
+    body = open(plain).read().splitlines()
+    with open(mm, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real symmetric\n% a comment\n\n" + body[0] + "\n")
+        for i, ln in enumerate(body[1:]):
+            f.write(ln + " 1.0\n")
+            if i == 3:
+                f.write("% comment between entries\n")
+    n1, ro1, ci1 = lz.read_text(plain)
+    n2, ro2, ci2 = lz.read_text(mm)
+    assert n1 == n2 == n and np.array_equal(ro1, ro) and np.array_equal(ci1, ci) and np.array_equal(ro2, ro) and np.array_equal(ci2, ci)
+    bad = str(tmp_path / "bad.mtx")
+    open(bad, "w").write("% only comments\n")
+    import pytest
+    with pytest.raises(lz.LzError):
+        lz.read_text(bad)
